@@ -1,0 +1,170 @@
+/*
+ * fftlines.h -- batched C-ABI of libfftlines_cuda (B200 / sm_100a).
+ *
+ * This is the generalisation of the reference's per-tick spectrum chain to
+ * batched STFT.  The reference has no such entry points: it runs ONE frame per
+ * WM_TIMER tick inside WndProc (reference fft_lines/fft_lines.c:186-236,281).
+ * Each function below cites the reference lines whose work it performs for
+ * many frames at once.  The single-frame drop-in entry points of the reference
+ * itself live in fft_calculate.h and beatDetector.h next to this file.
+ *
+ * Plain C: pointers, sizes, PODs.  No torch / C++ types cross this boundary.
+ * There is NO CPU fallback: every compute call fails with FFTL_ERR_CUDA (and
+ * latches the error, see fftl_last_error) when no usable CUDA device exists.
+ */
+#ifndef FFTLINES_H
+#define FFTLINES_H
+
+#include <stdint.h>
+
+#ifdef __cplusplus
+extern "C" {
+#endif
+
+#define FFTL_VERSION 100
+
+/* ---- status codes ------------------------------------------------------ */
+enum {
+    FFTL_OK            = 0,
+    FFTL_ERR_ARG       = 1,  /* bad argument / unsupported configuration      */
+    FFTL_ERR_CUDA      = 2,  /* CUDA runtime error (no device, launch, copy)  */
+    FFTL_ERR_NOMEM     = 3,  /* host or device allocation failed              */
+    FFTL_ERR_STATE     = 4   /* call sequence error (e.g. execute before init)*/
+};
+
+/* ---- configuration ----------------------------------------------------- */
+enum { FFTL_WINDOW_RECT = 0, FFTL_WINDOW_HANN = 1 };
+enum { FFTL_BINNING_LINEAR = 0, FFTL_BINNING_LOG = 1 };
+
+/* Reference constants (fft_lines/settingsFile.h:4-13, beatDetector.c:6). */
+#define FFTL_BEAT_SAMPLES   160   /* NUMBER_OF_SAMPLES, beatDetector.c:6      */
+#define FFTL_TEMPO_RING     256   /* DEFAULT_BEATBBUFFERSIZE, settingsFile.h:11 */
+#define FFTL_MAX_BARS       4096
+#define FFTL_MAX_SG_HALF    8
+
+typedef struct fftl_config {
+    int32_t n;              /* window / FFT size: 256,512,...,16384 (reference: N=2048, global.h:3) */
+    int32_t hop;            /* samples between frame starts (reference: whatever WASAPI delivered)   */
+    int32_t bars;           /* bar count B (reference barCount 100..1000, settingsFile.h:4-5)       */
+    int32_t window;         /* FFTL_WINDOW_RECT = reference behaviour (fft_lines.c:190-194)         */
+    int32_t binning;        /* FFTL_BINNING_LINEAR = reference: bar i = bin i (fft_lines.c:199-203) */
+    int32_t sg_half;        /* Savitzky-Golay half width w (0 = off = reference)                    */
+    int32_t sg_degree;      /* SG polynomial degree d (< 2w+1)                                      */
+    int32_t circle;         /* nonzero: +10 on every height (fft_lines.c:204-207)                   */
+    float   zoom;           /* height = |X| * zoom (fft_lines.c:202; default 1e-4 settingsFile.h:13) */
+    float   sample_rate;    /* Hz; only used by LOG binning and tempo (timeDelta = hop/sample_rate) */
+    float   fmin;           /* LOG binning lower edge, Hz                                            */
+    float   fmax;           /* LOG binning upper edge, Hz                                            */
+    int32_t beat_bars[4];   /* bar indices averaged into the band energy; reference {3,4,5,6}
+                               (fft_lines.c:281)                                                     */
+    int32_t bass_bin;       /* FFT bin whose magnitude feeds the tempo ring; reference 4
+                               (beatDetector.c:53)                                                   */
+    int32_t strict_int;     /* 1: (int) casts overflow to INT32_MIN like x86 cvtt*2si (what the
+                               reference binary does); 0: saturate                                   */
+    int32_t reserved[3];
+} fftl_config;
+
+/* Per (channel, frame) beat record.
+ *  w, thr, beat_value : AddBeatSample state after the frame (beatDetector.c:30-44)
+ *  flag               : thr > 0 && w > thr (the reference has no boolean; this is ratio > 1)
+ *  bass               : (int)|X[bass_bin]| written to the tempo ring (beatDetector.c:53)
+ *  peak_index         : peaks[highestpeaknumber] (beatDetector.c:78-103)
+ *  movement_per_sec   : N * timeDelta * peak_index (beatDetector.c:105), timeDelta = hop/fs
+ */
+typedef struct fftl_beat {
+    int32_t w;
+    int32_t thr;
+    int32_t beat_value;
+    int32_t flag;
+    int32_t bass;
+    int32_t peak_index;
+    float   movement_per_sec;
+    int32_t reserved;
+} fftl_beat;
+
+/* Fills *cfg with the reference's behaviour ("parity mode"): RECT window,
+ * LINEAR binning, no smoothing, zoom 1e-4, beat bars 3..6, bass bin 4. */
+void fftl_config_reference(fftl_config* cfg, int32_t n, int32_t hop, int32_t bars);
+/* "Extended mode": Hann, LOG binning fmin..fmax, SG (w=3,d=2). Semantics are
+ * defined by this repo's oracle; the reference has none of these stages. */
+void fftl_config_extended(fftl_config* cfg, int32_t n, int32_t hop, int32_t bars,
+                          float sample_rate, float fmin, float fmax);
+/* FFTL_OK or FFTL_ERR_ARG (and latches a message). */
+int  fftl_config_validate(const fftl_config* cfg);
+
+/* Host-side tables derived from a config (also what the device uses).
+ * lo/hi: bars entries; bar b = mean(|X[k]|, lo[b] <= k < hi[b]).            */
+int  fftl_build_bins(const fftl_config* cfg, int32_t* lo, int32_t* hi);
+/* coef: (2w+1) rows x (2w+1) taps, row p = weights that evaluate the fitted
+ * polynomial at window position p; interior points use row w.               */
+int  fftl_build_sg(int32_t sg_half, int32_t sg_degree, float* coef);
+
+/* ---- batched STFT handle ----------------------------------------------- */
+typedef struct fftl_stft fftl_stft;
+
+/* device < 0: current device. Creates stream, uploads tables. */
+int     fftl_stft_create(const fftl_config* cfg, int device, fftl_stft** out);
+void    fftl_stft_destroy(fftl_stft* h);
+/* F = floor((samples - n)/hop) + 1, or 0. */
+int64_t fftl_stft_num_frames(const fftl_stft* h, int64_t samples_per_channel);
+
+/* PCM addressing: sample s of channel c is pcm[c*channel_stride + s*sample_stride]
+ * (planar: channel_stride = samples, sample_stride = 1; interleaved: 1, channels).
+ * Frames [frame_begin, frame_end) of every channel are produced:
+ *   bars     [channels][frame_end-frame_begin][bars] float   (height before the (int) cast)
+ *   bars_i32 same shape, int32, the reference's BARINFO.height      (may be NULL)
+ *   beat     [channels][frame_end-frame_begin]                       (may be NULL)
+ * Beat outputs are those of a reference run started at frame 0: the up-to-255
+ * frames before frame_begin are recomputed internally (frame-range shards need
+ * no neighbour exchange).
+ * Restates for all frames: fft_lines.c:190-231 (bars), :281 + beatDetector.c:30-44
+ * (band energy), :233-236 + beatDetector.c:51-106 (tempo).                       */
+int fftl_stft_run_device(fftl_stft* h, const int16_t* pcm_dev, int32_t channels,
+                         int64_t samples_per_channel, int64_t channel_stride,
+                         int64_t sample_stride, int64_t frame_begin, int64_t frame_end,
+                         float* bars_dev, int32_t* bars_i32_dev, fftl_beat* beat_dev,
+                         void* cuda_stream /* cudaStream_t or NULL = handle's stream */);
+
+/* Same, host buffers.  Copies are chunked by frame range and overlapped with
+ * the kernels on three streams; buffers from fftl_host_alloc (pinned) make the
+ * copies asynchronous. Returns after all outputs are in host memory.          */
+int fftl_stft_run(fftl_stft* h, const int16_t* pcm_host, int32_t channels,
+                  int64_t samples_per_channel, int64_t channel_stride,
+                  int64_t sample_stride, int64_t frame_begin, int64_t frame_end,
+                  float* bars_host, int32_t* bars_i32_host, fftl_beat* beat_host);
+
+/* Number of kernel launches issued by this handle since creation. */
+int64_t fftl_stft_launch_count(const fftl_stft* h);
+/* Device time (ms, CUDA events on the launching stream) of the last
+ * fftl_stft_run_device: whole call, and the dominant stft_bars kernel(s) only.
+ * Forces a stream sync. */
+int fftl_stft_last_timing(fftl_stft* h, float* total_ms, float* bars_kernel_ms);
+
+/* Pinned host memory helpers. */
+void* fftl_host_alloc(uint64_t bytes);
+void  fftl_host_free(void* p);
+
+/* On-device synthetic PCM: sweep + Philox noise + AM bass tone.
+ * Writes planar int16 [channels][samples] at pcm_dev; sample index offset
+ * `first_sample` lets shards generate their own range.                        */
+int fftl_synth_pcm_device(int16_t* pcm_dev, int32_t channels, int64_t samples,
+                          int64_t channel_stride, int64_t first_sample,
+                          float sample_rate, uint32_t seed, void* cuda_stream);
+
+/* ---- errors / info ----------------------------------------------------- */
+int         fftl_last_error(void);          /* sticky until fftl_clear_error */
+const char* fftl_last_error_string(void);
+void        fftl_clear_error(void);
+int         fftl_version(void);
+int         fftl_device_count(void);        /* 0 when no CUDA device is usable */
+
+/* Compat (single-frame) layer knobs; see fft_calculate.h / beatDetector.h. */
+int  fftl_set_n(int32_t n);                 /* default 2048 = reference N (global.h:3) */
+int  fftl_get_n(void);
+void fftl_compat_reset_beat(void);          /* zero AddBeatSample / tempo state */
+int64_t fftl_compat_launch_count(void);
+
+#ifdef __cplusplus
+}
+#endif
+#endif /* FFTLINES_H */

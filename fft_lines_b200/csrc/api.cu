@@ -1,0 +1,866 @@
+// api.cu -- host side of libfftlines_cuda: the C-ABI declared in
+// include/fftlines.h, include/fft_calculate.h and include/beatDetector.h.
+//
+// No CPU fallback anywhere: if CUDA is unusable every compute entry point
+// fails and latches the error.
+#include <cuda_runtime.h>
+#include <math.h>
+#include <stdarg.h>
+#include <stdio.h>
+#include <stdlib.h>
+#include <string.h>
+#include <mutex>
+#include <vector>
+
+#include "kernels.cuh"
+#include "../../include/fft_calculate.h"
+#include "../../include/beatDetector.h"
+
+using namespace fftl;
+
+// ------------------------------------------------------------------ errors
+static int g_err = FFTL_OK;
+static char g_errmsg[512] = "";
+static std::mutex g_err_mu;
+
+static int set_error(int code, const char* fmt, ...)
+{
+    std::lock_guard<std::mutex> lk(g_err_mu);
+    g_err = code;
+    va_list ap;
+    va_start(ap, fmt);
+    vsnprintf(g_errmsg, sizeof(g_errmsg), fmt, ap);
+    va_end(ap);
+    return code;
+}
+
+#define CUDA_TRY(expr)                                                                              \
+    do {                                                                                            \
+        cudaError_t e__ = (expr);                                                                   \
+        if (e__ != cudaSuccess)                                                                     \
+            return set_error(FFTL_ERR_CUDA, "%s failed: %s (%s:%d)", #expr, cudaGetErrorString(e__), \
+                             __FILE__, __LINE__);                                                   \
+    } while (0)
+
+extern "C" int fftl_last_error(void) { return g_err; }
+extern "C" const char* fftl_last_error_string(void) { return g_errmsg; }
+extern "C" void fftl_clear_error(void)
+{
+    std::lock_guard<std::mutex> lk(g_err_mu);
+    g_err = FFTL_OK;
+    g_errmsg[0] = 0;
+}
+extern "C" int fftl_version(void) { return FFTL_VERSION; }
+extern "C" int fftl_device_count(void)
+{
+    int n = 0;
+    if (cudaGetDeviceCount(&n) != cudaSuccess) {
+        cudaGetLastError();
+        return 0;
+    }
+    return n;
+}
+
+// ------------------------------------------------------------------ config
+extern "C" void fftl_config_reference(fftl_config* c, int32_t n, int32_t hop, int32_t bars)
+{
+    memset(c, 0, sizeof(*c));
+    c->n = n;
+    c->hop = hop;
+    c->bars = bars;
+    c->window = FFTL_WINDOW_RECT;     // fft_lines.c:190-194: raw samples
+    c->binning = FFTL_BINNING_LINEAR; // fft_lines.c:199-203: bar i = bin i
+    c->zoom = 1e-4f;                  // DEFAULT_ZOOM, settingsFile.h:13
+    c->sample_rate = 48000.0f;
+    c->fmin = 20.0f;
+    c->fmax = 20000.0f;
+    c->beat_bars[0] = 3;              // fft_lines.c:281
+    c->beat_bars[1] = 4;
+    c->beat_bars[2] = 5;
+    c->beat_bars[3] = 6;
+    c->bass_bin = 4;                  // beatDetector.c:53
+    c->strict_int = 1;
+}
+
+extern "C" void fftl_config_extended(fftl_config* c, int32_t n, int32_t hop, int32_t bars, float sample_rate, float fmin,
+                                     float fmax)
+{
+    fftl_config_reference(c, n, hop, bars);
+    c->window = FFTL_WINDOW_HANN;
+    c->binning = FFTL_BINNING_LOG;
+    c->sg_half = 3;
+    c->sg_degree = 2;
+    c->sample_rate = sample_rate;
+    c->fmin = fmin;
+    c->fmax = fmax;
+}
+
+static bool pow2(int n) { return n > 0 && !(n & (n - 1)); }
+
+extern "C" int fftl_config_validate(const fftl_config* c)
+{
+    if (!c) return set_error(FFTL_ERR_ARG, "config is NULL");
+    if (!pow2(c->n) || c->n < 256 || c->n > 16384) return set_error(FFTL_ERR_ARG, "n=%d: need a power of two in 256..16384", c->n);
+    if (c->hop < 1) return set_error(FFTL_ERR_ARG, "hop=%d must be >= 1", c->hop);
+    if (c->bars < 1 || c->bars > FFTL_MAX_BARS) return set_error(FFTL_ERR_ARG, "bars=%d out of 1..%d", c->bars, FFTL_MAX_BARS);
+    if (c->window != FFTL_WINDOW_RECT && c->window != FFTL_WINDOW_HANN) return set_error(FFTL_ERR_ARG, "unknown window %d", c->window);
+    if (!(c->sample_rate > 0)) return set_error(FFTL_ERR_ARG, "sample_rate must be positive");
+    if (c->binning == FFTL_BINNING_LINEAR) {
+        if (c->bars > c->n / 2 + 1) return set_error(FFTL_ERR_ARG, "LINEAR binning: bars=%d exceeds n/2+1=%d", c->bars, c->n / 2 + 1);
+    } else if (c->binning == FFTL_BINNING_LOG) {
+        if (!(c->fmin > 0) || !(c->fmax > c->fmin) || c->fmax > 0.5f * c->sample_rate)
+            return set_error(FFTL_ERR_ARG, "LOG binning: need 0 < fmin < fmax <= sample_rate/2");
+    } else
+        return set_error(FFTL_ERR_ARG, "unknown binning %d", c->binning);
+    if (c->sg_half < 0 || c->sg_half > FFTL_MAX_SG_HALF) return set_error(FFTL_ERR_ARG, "sg_half=%d out of 0..%d", c->sg_half, FFTL_MAX_SG_HALF);
+    if (c->sg_half > 0) {
+        if (c->sg_degree < 0 || c->sg_degree > 2 * c->sg_half) return set_error(FFTL_ERR_ARG, "sg_degree=%d out of 0..%d", c->sg_degree, 2 * c->sg_half);
+        if (c->bars < 2 * c->sg_half + 1) return set_error(FFTL_ERR_ARG, "SG window wider than the bar vector");
+    }
+    for (int i = 0; i < 4; i++)
+        if (c->beat_bars[i] < 0 || c->beat_bars[i] >= c->bars) return set_error(FFTL_ERR_ARG, "beat_bars[%d]=%d outside 0..bars-1", i, c->beat_bars[i]);
+    if (c->bass_bin < 0 || c->bass_bin > c->n / 2) return set_error(FFTL_ERR_ARG, "bass_bin=%d outside 0..n/2", c->bass_bin);
+    return FFTL_OK;
+}
+
+extern "C" int fftl_build_bins(const fftl_config* c, int32_t* lo, int32_t* hi)
+{
+    int rc = fftl_config_validate(c);
+    if (rc) return rc;
+    const int top = c->n / 2 + 1;
+    if (c->binning == FFTL_BINNING_LINEAR) {
+        for (int b = 0; b < c->bars; b++) {
+            lo[b] = b;
+            hi[b] = b + 1;
+        }
+        return FFTL_OK;
+    }
+    // geometric band edges fmin..fmax; a bar covers the bins whose index lies
+    // between its two edges (at least one bin, low bars may repeat a bin)
+    const double ratio = (double)c->fmax / (double)c->fmin;
+    const double bins_per_hz = (double)c->n / (double)c->sample_rate;
+    for (int b = 0; b < c->bars; b++) {
+        double edge_lo = (double)c->fmin * pow(ratio, (double)b / (double)c->bars);
+        double edge_hi = (double)c->fmin * pow(ratio, (double)(b + 1) / (double)c->bars);
+        int first = (int)floor(edge_lo * bins_per_hz);
+        int last = (int)floor(edge_hi * bins_per_hz);
+        first = first < 0 ? 0 : (first > top - 1 ? top - 1 : first);
+        if (last <= first) last = first + 1;
+        if (last > top) last = top;
+        lo[b] = first;
+        hi[b] = last;
+    }
+    return FFTL_OK;
+}
+
+// Savitzky-Golay via orthonormal (Gram-Schmidt) polynomials on x=-w..w:
+// P = Q Q^T with Q the orthonormal basis of degree <= d.
+extern "C" int fftl_build_sg(int32_t w, int32_t d, float* coef)
+{
+    if (w < 1 || w > FFTL_MAX_SG_HALF || d < 0 || d > 2 * w) return set_error(FFTL_ERR_ARG, "bad SG parameters w=%d d=%d", w, d);
+    const int m = 2 * w + 1;
+    std::vector<std::vector<long double>> q;
+    for (int j = 0; j <= d; j++) {
+        std::vector<long double> col(m);
+        for (int i = 0; i < m; i++) col[i] = powl((long double)(i - w) / (long double)w, j);
+        for (int pass = 0; pass < 2; pass++) // re-orthogonalise once
+            for (auto& prev : q) {
+                long double dot = 0;
+                for (int i = 0; i < m; i++) dot += prev[i] * col[i];
+                for (int i = 0; i < m; i++) col[i] -= dot * prev[i];
+            }
+        long double nrm = 0;
+        for (int i = 0; i < m; i++) nrm += col[i] * col[i];
+        nrm = sqrtl(nrm);
+        if (nrm < 1e-18L) return set_error(FFTL_ERR_ARG, "SG basis is degenerate");
+        for (int i = 0; i < m; i++) col[i] /= nrm;
+        q.push_back(col);
+    }
+    for (int i = 0; i < m; i++)
+        for (int k = 0; k < m; k++) {
+            long double s = 0;
+            for (auto& col : q) s += col[i] * col[k];
+            coef[i * m + k] = (float)s;
+        }
+    return FFTL_OK;
+}
+
+// ------------------------------------------------------------------ tables
+static void fill_twiddles(std::vector<float2>& tw, int n)
+{
+    tw.resize(n);
+    for (int m = 0; m < n; m++) {
+        // exact octant symmetry is not needed; double sincos of the exact angle
+        double a = -2.0 * M_PI * (double)m / (double)n;
+        tw[m] = make_float2((float)cos(a), (float)sin(a));
+    }
+}
+
+template <int N> static cudaError_t launch_stft(const StftParams& p, int channels, long long pairs, cudaStream_t st)
+{
+    using Sh = StftShape<N>;
+    size_t smem = Sh::smem_bytes(p.bars_n);
+    if (smem > 48 * 1024) { // opt-in is per device, so no process-wide cache
+        cudaError_t e = cudaFuncSetAttribute(stft_bars_kernel<N>, cudaFuncAttributeMaxDynamicSharedMemorySize, (int)smem);
+        if (e != cudaSuccess) return e;
+    }
+    long long blocks = (pairs + Sh::PAIRS - 1) / Sh::PAIRS;
+    if (blocks <= 0) return cudaSuccess;
+    dim3 grid((unsigned)blocks, (unsigned)channels);
+    stft_bars_kernel<N><<<grid, Sh::THREADS, smem, st>>>(p);
+    return cudaGetLastError();
+}
+
+static cudaError_t dispatch_stft(int n, const StftParams& p, int channels, long long pairs, cudaStream_t st)
+{
+    switch (n) {
+    case 256: return launch_stft<256>(p, channels, pairs, st);
+    case 512: return launch_stft<512>(p, channels, pairs, st);
+    case 1024: return launch_stft<1024>(p, channels, pairs, st);
+    case 2048: return launch_stft<2048>(p, channels, pairs, st);
+    case 4096: return launch_stft<4096>(p, channels, pairs, st);
+    case 8192: return launch_stft<8192>(p, channels, pairs, st);
+    case 16384: return launch_stft<16384>(p, channels, pairs, st);
+    }
+    return cudaErrorInvalidValue;
+}
+
+template <int N> static cudaError_t launch_c2c(const float2* in, float2* out, const float2* tw, cudaStream_t st)
+{
+    constexpr int VPT = (N >= 16384) ? 32 : 16;
+    size_t smem = padded_size(N) * sizeof(float2);
+    if (smem > 48 * 1024) {
+        cudaError_t e = cudaFuncSetAttribute(c2c_kernel<N>, cudaFuncAttributeMaxDynamicSharedMemorySize, (int)smem);
+        if (e != cudaSuccess) return e;
+    }
+    c2c_kernel<N><<<1, N / VPT, smem, st>>>(in, out, tw);
+    return cudaGetLastError();
+}
+
+static cudaError_t dispatch_c2c(int n, const float2* in, float2* out, const float2* tw, cudaStream_t st)
+{
+    switch (n) {
+    case 256: return launch_c2c<256>(in, out, tw, st);
+    case 512: return launch_c2c<512>(in, out, tw, st);
+    case 1024: return launch_c2c<1024>(in, out, tw, st);
+    case 2048: return launch_c2c<2048>(in, out, tw, st);
+    case 4096: return launch_c2c<4096>(in, out, tw, st);
+    case 8192: return launch_c2c<8192>(in, out, tw, st);
+    case 16384: return launch_c2c<16384>(in, out, tw, st);
+    }
+    return cudaErrorInvalidValue;
+}
+
+// ------------------------------------------------------------------ handle
+static const int TIMING_SLOTS = 64;
+
+struct fftl_stft {
+    fftl_config cfg;
+    int device;
+    cudaStream_t stream;            // compute
+    cudaStream_t s_h2d, s_d2h;      // copy streams of the host-buffer path
+    float* d_window;
+    float2* d_tw;
+    float2* d_tw256;
+    int* d_lo;
+    int* d_hi;
+    float* d_sg;
+    int* d_aux;                     // [2][channels][nf_aux] (w then bass)
+    size_t aux_capacity;            // ints
+    int64_t launches;
+    // device timing of run_device calls (ring of event triples)
+    cudaEvent_t ev[TIMING_SLOTS][3];
+    int timing_count;               // calls recorded since last reset (saturates at TIMING_SLOTS)
+    int timing_next;
+    // staging of the host-buffer path
+    void* d_stage[2][4];            // per slot: pcm, bars, bars_i32, beat
+    size_t stage_bytes[2][4];
+    cudaEvent_t ev_h2d[2], ev_comp[2], ev_d2h[2];
+};
+
+static int ensure_bytes(void** p, size_t* cap, size_t need)
+{
+    if (*cap >= need) return FFTL_OK;
+    if (*p) cudaFree(*p);
+    *p = nullptr;
+    *cap = 0;
+    cudaError_t e = cudaMalloc(p, need);
+    if (e != cudaSuccess) return set_error(FFTL_ERR_NOMEM, "cudaMalloc(%zu) failed: %s", need, cudaGetErrorString(e));
+    *cap = need;
+    return FFTL_OK;
+}
+
+extern "C" int fftl_stft_create(const fftl_config* cfg, int device, fftl_stft** out)
+{
+    if (!out) return set_error(FFTL_ERR_ARG, "out is NULL");
+    *out = nullptr;
+    int rc = fftl_config_validate(cfg);
+    if (rc) return rc;
+    int ndev = 0;
+    CUDA_TRY(cudaGetDeviceCount(&ndev));
+    if (ndev < 1) return set_error(FFTL_ERR_CUDA, "no CUDA device (libfftlines_cuda has no CPU fallback)");
+    if (device < 0) CUDA_TRY(cudaGetDevice(&device));
+    if (device >= ndev) return set_error(FFTL_ERR_ARG, "device %d out of range", device);
+    CUDA_TRY(cudaSetDevice(device));
+    fftl_stft* h = (fftl_stft*)calloc(1, sizeof(fftl_stft));
+    if (!h) return set_error(FFTL_ERR_NOMEM, "out of host memory");
+    h->cfg = *cfg;
+    h->device = device;
+    const int n = cfg->n, B = cfg->bars;
+    std::vector<float2> tw, tw256;
+    fill_twiddles(tw, n);
+    fill_twiddles(tw256, FFTL_TEMPO_RING);
+    std::vector<int32_t> lo(B), hi(B);
+    fftl_build_bins(cfg, lo.data(), hi.data());
+#define H_TRY(expr)                                                                                  \
+    do {                                                                                             \
+        cudaError_t e__ = (expr);                                                                    \
+        if (e__ != cudaSuccess) {                                                                    \
+            set_error(FFTL_ERR_CUDA, "%s failed: %s", #expr, cudaGetErrorString(e__));               \
+            fftl_stft_destroy(h);                                                                    \
+            return FFTL_ERR_CUDA;                                                                    \
+        }                                                                                            \
+    } while (0)
+    H_TRY(cudaStreamCreateWithFlags(&h->stream, cudaStreamNonBlocking));
+    H_TRY(cudaStreamCreateWithFlags(&h->s_h2d, cudaStreamNonBlocking));
+    H_TRY(cudaStreamCreateWithFlags(&h->s_d2h, cudaStreamNonBlocking));
+    H_TRY(cudaMalloc(&h->d_tw, sizeof(float2) * n));
+    H_TRY(cudaMemcpy(h->d_tw, tw.data(), sizeof(float2) * n, cudaMemcpyHostToDevice));
+    H_TRY(cudaMalloc(&h->d_tw256, sizeof(float2) * FFTL_TEMPO_RING));
+    H_TRY(cudaMemcpy(h->d_tw256, tw256.data(), sizeof(float2) * FFTL_TEMPO_RING, cudaMemcpyHostToDevice));
+    H_TRY(cudaMalloc(&h->d_lo, sizeof(int) * B));
+    H_TRY(cudaMalloc(&h->d_hi, sizeof(int) * B));
+    H_TRY(cudaMemcpy(h->d_lo, lo.data(), sizeof(int) * B, cudaMemcpyHostToDevice));
+    H_TRY(cudaMemcpy(h->d_hi, hi.data(), sizeof(int) * B, cudaMemcpyHostToDevice));
+    if (cfg->window == FFTL_WINDOW_HANN) {
+        std::vector<float> win(n);
+        for (int i = 0; i < n; i++) win[i] = (float)(0.5 - 0.5 * cos(2.0 * M_PI * (double)i / (double)n)); // periodic Hann
+        H_TRY(cudaMalloc(&h->d_window, sizeof(float) * n));
+        H_TRY(cudaMemcpy(h->d_window, win.data(), sizeof(float) * n, cudaMemcpyHostToDevice));
+    }
+    if (cfg->sg_half > 0) {
+        int m = 2 * cfg->sg_half + 1;
+        std::vector<float> sg(m * m);
+        if (fftl_build_sg(cfg->sg_half, cfg->sg_degree, sg.data())) {
+            fftl_stft_destroy(h);
+            return FFTL_ERR_ARG;
+        }
+        H_TRY(cudaMalloc(&h->d_sg, sizeof(float) * m * m));
+        H_TRY(cudaMemcpy(h->d_sg, sg.data(), sizeof(float) * m * m, cudaMemcpyHostToDevice));
+    }
+    for (int i = 0; i < TIMING_SLOTS; i++)
+        for (int k = 0; k < 3; k++) H_TRY(cudaEventCreate(&h->ev[i][k]));
+    for (int i = 0; i < 2; i++) {
+        H_TRY(cudaEventCreateWithFlags(&h->ev_h2d[i], cudaEventDisableTiming));
+        H_TRY(cudaEventCreateWithFlags(&h->ev_comp[i], cudaEventDisableTiming));
+        H_TRY(cudaEventCreateWithFlags(&h->ev_d2h[i], cudaEventDisableTiming));
+    }
+#undef H_TRY
+    *out = h;
+    return FFTL_OK;
+}
+
+extern "C" void fftl_stft_destroy(fftl_stft* h)
+{
+    if (!h) return;
+    cudaSetDevice(h->device);
+    if (h->stream) cudaStreamSynchronize(h->stream);
+    if (h->s_h2d) cudaStreamSynchronize(h->s_h2d);
+    if (h->s_d2h) cudaStreamSynchronize(h->s_d2h);
+    cudaFree(h->d_window);
+    cudaFree(h->d_tw);
+    cudaFree(h->d_tw256);
+    cudaFree(h->d_lo);
+    cudaFree(h->d_hi);
+    cudaFree(h->d_sg);
+    cudaFree(h->d_aux);
+    for (int i = 0; i < 2; i++)
+        for (int k = 0; k < 4; k++) cudaFree(h->d_stage[i][k]);
+    for (int i = 0; i < TIMING_SLOTS; i++)
+        for (int k = 0; k < 3; k++)
+            if (h->ev[i][k]) cudaEventDestroy(h->ev[i][k]);
+    for (int i = 0; i < 2; i++) {
+        if (h->ev_h2d[i]) cudaEventDestroy(h->ev_h2d[i]);
+        if (h->ev_comp[i]) cudaEventDestroy(h->ev_comp[i]);
+        if (h->ev_d2h[i]) cudaEventDestroy(h->ev_d2h[i]);
+    }
+    if (h->stream) cudaStreamDestroy(h->stream);
+    if (h->s_h2d) cudaStreamDestroy(h->s_h2d);
+    if (h->s_d2h) cudaStreamDestroy(h->s_d2h);
+    cudaGetLastError();
+    free(h);
+}
+
+extern "C" int64_t fftl_stft_num_frames(const fftl_stft* h, int64_t samples)
+{
+    if (!h || samples < h->cfg.n) return 0;
+    return (samples - h->cfg.n) / h->cfg.hop + 1;
+}
+
+extern "C" int64_t fftl_stft_launch_count(const fftl_stft* h) { return h ? h->launches : 0; }
+
+// Core: frames [fb, fe) of every channel; aux (w, bass) indexed from aux_base
+// with per-channel stride nf_aux.  `compute_from` <= fb is where this call
+// starts computing aux (frames before it must already be in the aux arrays).
+static int run_range(fftl_stft* h, const int16_t* pcm, int channels, int64_t cstride, int64_t sstride, int64_t compute_from,
+                     int64_t fb, int64_t fe, int64_t out_base, int64_t nf_emit, int64_t aux_base, int64_t nf_aux, float* bars,
+                     int32_t* bars_i32, bool aux, fftl_beat* beat, cudaStream_t st, cudaEvent_t* evs)
+{
+    const fftl_config& c = h->cfg;
+    StftParams p;
+    memset(&p, 0, sizeof(p));
+    p.pcm = pcm;
+    p.channel_stride = cstride;
+    p.sample_stride = sstride;
+    p.frame0 = compute_from;
+    p.frame_emit = fb;
+    p.frame_end = fe;
+    p.nf_emit = nf_emit;
+    p.nf_aux = nf_aux;
+    p.aux_base = aux_base;
+    p.window = h->d_window;
+    p.tw = h->d_tw;
+    p.lo = h->d_lo;
+    p.hi = h->d_hi;
+    p.sg = h->d_sg;
+    // outputs are addressed relative to frame_emit inside the kernel
+    p.bars = bars + (fb - out_base) * (int64_t)c.bars;
+    p.bars_i32 = bars_i32 ? bars_i32 + (fb - out_base) * (int64_t)c.bars : nullptr;
+    p.aux_w = aux ? h->d_aux : nullptr;
+    p.aux_bass = aux ? h->d_aux + (size_t)channels * nf_aux : nullptr;
+    p.hop = c.hop;
+    p.bars_n = c.bars;
+    p.sg_half = c.sg_half;
+    p.strict = c.strict_int;
+    p.bass_bin = c.bass_bin;
+    for (int i = 0; i < 4; i++) p.beat_bars[i] = c.beat_bars[i];
+    p.zoom = c.zoom;
+    p.circle_add = c.circle ? 10.0f : 0.0f; // fft_lines.c:204-207
+    long long pairs = (fe - compute_from + 1) / 2;
+    if (evs) CUDA_TRY(cudaEventRecord(evs[0], st));
+    CUDA_TRY(dispatch_stft(c.n, p, channels, pairs, st));
+    h->launches++;
+    if (evs) CUDA_TRY(cudaEventRecord(evs[1], st));
+    if (beat && fe > fb) {
+        BeatParams bp;
+        bp.aux_w = p.aux_w;
+        bp.aux_bass = p.aux_bass;
+        bp.out = beat + (fb - out_base);
+        bp.tw256 = h->d_tw256;
+        bp.aux_base = aux_base;
+        bp.nf_aux = nf_aux;
+        bp.frame_emit = fb;
+        bp.frame_end = fe;
+        bp.nf_emit = nf_emit;
+        float dt = (float)c.hop / c.sample_rate;  // timeDelta of a batch run (fft_lines.c:265 uses wall clock)
+        bp.n_times_dt = (float)c.n * dt;          // beatDetector.c:105, left-to-right in float
+        bp.strict = c.strict_int;
+        dim3 grid((unsigned)((fe - fb + BEAT_FRAMES_PER_CTA - 1) / BEAT_FRAMES_PER_CTA), (unsigned)channels);
+        beat_post_kernel<<<grid, 256, 0, st>>>(bp);
+        CUDA_TRY(cudaGetLastError());
+        h->launches++;
+    }
+    if (evs) CUDA_TRY(cudaEventRecord(evs[2], st));
+    return FFTL_OK;
+}
+
+static int check_run_args(fftl_stft* h, const void* pcm, int channels, int64_t samples, int64_t fb, int64_t fe, const void* bars)
+{
+    if (!h) return set_error(FFTL_ERR_ARG, "handle is NULL");
+    if (!pcm || !bars) return set_error(FFTL_ERR_ARG, "pcm and bars must not be NULL");
+    if (channels < 1 || channels > 65535) return set_error(FFTL_ERR_ARG, "channels=%d out of 1..65535", channels);
+    int64_t F = fftl_stft_num_frames(h, samples);
+    if (fb < 0 || fe < fb || fe > F) return set_error(FFTL_ERR_ARG, "frame range [%lld,%lld) outside [0,%lld]", (long long)fb, (long long)fe, (long long)F);
+    return FFTL_OK;
+}
+
+extern "C" int fftl_stft_run_device(fftl_stft* h, const int16_t* pcm, int32_t channels, int64_t samples, int64_t cstride,
+                                    int64_t sstride, int64_t fb, int64_t fe, float* bars, int32_t* bars_i32, fftl_beat* beat,
+                                    void* cuda_stream)
+{
+    int rc = check_run_args(h, pcm, channels, samples, fb, fe, bars);
+    if (rc) return rc;
+    if (fe == fb) return FFTL_OK;
+    CUDA_TRY(cudaSetDevice(h->device));
+    cudaStream_t st = cuda_stream ? (cudaStream_t)cuda_stream : h->stream;
+    int64_t warm = fb;
+    if (beat) {
+        warm = fb - (FFTL_TEMPO_RING - 1);
+        if (warm < 0) warm = 0;
+        // keep frame pairs aligned to even offsets from `warm`
+    }
+    int64_t nf_aux = fe - warm;
+    if (beat) {
+        size_t need = sizeof(int) * 2 * (size_t)channels * (size_t)nf_aux;
+        if (h->aux_capacity < need) {
+            CUDA_TRY(cudaStreamSynchronize(st));
+            void* pv = h->d_aux;
+            rc = ensure_bytes(&pv, &h->aux_capacity, need);
+            h->d_aux = (int*)pv;
+            if (rc) return rc;
+        }
+    }
+    cudaEvent_t* evs = h->ev[h->timing_next];
+    rc = run_range(h, pcm, channels, cstride, sstride, warm, fb, fe, fb, fe - fb, warm, nf_aux, bars, bars_i32, beat != nullptr, beat, st, evs);
+    if (rc) return rc;
+    h->timing_next = (h->timing_next + 1) % TIMING_SLOTS;
+    if (h->timing_count < TIMING_SLOTS) h->timing_count++;
+    return FFTL_OK;
+}
+
+// Sum of device times over the run_device calls recorded since the last call
+// of this function (at most TIMING_SLOTS).  Synchronises the events.
+extern "C" int fftl_stft_timing(fftl_stft* h, int32_t* calls, float* total_ms, float* bars_kernel_ms)
+{
+    if (!h) return set_error(FFTL_ERR_ARG, "handle is NULL");
+    CUDA_TRY(cudaSetDevice(h->device));
+    float tot = 0, bars = 0;
+    int n = h->timing_count;
+    for (int i = 0; i < n; i++) {
+        int slot = (h->timing_next - 1 - i + 2 * TIMING_SLOTS) % TIMING_SLOTS;
+        CUDA_TRY(cudaEventSynchronize(h->ev[slot][2]));
+        float a = 0, b = 0;
+        CUDA_TRY(cudaEventElapsedTime(&a, h->ev[slot][0], h->ev[slot][2]));
+        CUDA_TRY(cudaEventElapsedTime(&b, h->ev[slot][0], h->ev[slot][1]));
+        tot += a;
+        bars += b;
+    }
+    h->timing_count = 0;
+    if (total_ms) *total_ms = tot;
+    if (bars_kernel_ms) *bars_kernel_ms = bars;
+    if (calls) *calls = n;
+    return FFTL_OK;
+}
+
+// Host-buffer path: frame-range chunks, H2D / kernels / D2H overlapped on
+// three streams with two staging slots.
+extern "C" int fftl_stft_run(fftl_stft* h, const int16_t* pcm, int32_t channels, int64_t samples, int64_t cstride,
+                             int64_t sstride, int64_t fb, int64_t fe, float* bars, int32_t* bars_i32, fftl_beat* beat)
+{
+    int rc = check_run_args(h, pcm, channels, samples, fb, fe, bars);
+    if (rc) return rc;
+    if (fe == fb) return FFTL_OK;
+    if (sstride != 1 && !(sstride == channels && cstride == 1))
+        return set_error(FFTL_ERR_ARG, "host path supports planar (sample_stride 1) or interleaved (sample_stride = channels, channel_stride 1) PCM");
+    CUDA_TRY(cudaSetDevice(h->device));
+    const fftl_config& c = h->cfg;
+    const int B = c.bars, n = c.n, hop = c.hop;
+    const bool interleaved = (sstride != 1);
+    int64_t warm = fb;
+    if (beat) {
+        warm = fb - (FFTL_TEMPO_RING - 1);
+        if (warm < 0) warm = 0;
+    }
+    const int64_t nf_aux = fe - warm;
+    if (beat) {
+        size_t need = sizeof(int) * 2 * (size_t)channels * (size_t)nf_aux;
+        void* pv = h->d_aux;
+        CUDA_TRY(cudaStreamSynchronize(h->stream));
+        rc = ensure_bytes(&pv, &h->aux_capacity, need);
+        h->d_aux = (int*)pv;
+        if (rc) return rc;
+    }
+    // chunk size: ~64 MiB of bar output per slot, at least 512 frames, even
+    int64_t chunk = (int64_t)(64ll << 20) / ((int64_t)channels * B * 4);
+    if (chunk < 512) chunk = 512;
+    if (chunk > fe - warm) chunk = fe - warm;
+    chunk += chunk & 1;
+    const int64_t nf_total = fe - fb;
+    int slot = 0;
+    int64_t nchunks = 0;
+    for (int64_t a = warm; a < fe; a += chunk, slot ^= 1, nchunks++) {
+        int64_t b = a + chunk < fe ? a + chunk : fe; // compute frames [a,b)
+        int64_t ea = a > fb ? a : fb;                // emit frames [ea,b)
+        int64_t ne = b > ea ? b - ea : 0;
+        int64_t s0 = a * hop, s1 = (b - 1) * hop + n; // sample span per channel
+        int64_t span = s1 - s0;
+        size_t pcm_bytes = sizeof(int16_t) * (size_t)channels * span;
+        size_t bars_bytes = sizeof(float) * (size_t)channels * (size_t)(ne > 0 ? ne : 1) * B;
+        size_t beat_bytes = sizeof(fftl_beat) * (size_t)channels * (size_t)(ne > 0 ? ne : 1);
+        // the slot's previous D2H must be finished before its buffers are reused
+        if (nchunks >= 2) CUDA_TRY(cudaEventSynchronize(h->ev_d2h[slot]));
+        if ((rc = ensure_bytes(&h->d_stage[slot][0], &h->stage_bytes[slot][0], pcm_bytes))) return rc;
+        if ((rc = ensure_bytes(&h->d_stage[slot][1], &h->stage_bytes[slot][1], bars_bytes))) return rc;
+        if (bars_i32 && (rc = ensure_bytes(&h->d_stage[slot][2], &h->stage_bytes[slot][2], bars_bytes))) return rc;
+        if (beat && (rc = ensure_bytes(&h->d_stage[slot][3], &h->stage_bytes[slot][3], beat_bytes))) return rc;
+        int16_t* d_pcm = (int16_t*)h->d_stage[slot][0];
+        // H2D (the compute that last read this slot's pcm finished before its D2H did)
+        if (interleaved) {
+            CUDA_TRY(cudaMemcpyAsync(d_pcm, pcm + s0 * channels, pcm_bytes, cudaMemcpyHostToDevice, h->s_h2d));
+        } else {
+            for (int ch = 0; ch < channels; ch++)
+                CUDA_TRY(cudaMemcpyAsync(d_pcm + (size_t)ch * span, pcm + ch * cstride + s0, sizeof(int16_t) * span, cudaMemcpyHostToDevice, h->s_h2d));
+        }
+        CUDA_TRY(cudaEventRecord(h->ev_h2d[slot], h->s_h2d));
+        CUDA_TRY(cudaStreamWaitEvent(h->stream, h->ev_h2d[slot], 0));
+        // kernels: device pcm starts at sample s0, i.e. frame a
+        {
+            const int16_t* base = interleaved ? d_pcm - s0 * channels : d_pcm - s0;
+            int64_t dcs = interleaved ? 1 : span;
+            int64_t dss = interleaved ? channels : 1;
+            float* d_bars = (float*)h->d_stage[slot][1];
+            int32_t* d_i32 = bars_i32 ? (int32_t*)h->d_stage[slot][2] : nullptr;
+            fftl_beat* d_beat = beat ? (fftl_beat*)h->d_stage[slot][3] : nullptr;
+            if (ne > 0)
+                rc = run_range(h, base, channels, dcs, dss, a, ea, b, ea, ne, warm, nf_aux, d_bars, d_i32, beat != nullptr, d_beat, h->stream, nullptr);
+            else // pure beat warm-up chunk: band energy / bass only, nothing emitted
+                rc = run_range(h, base, channels, dcs, dss, a, b, b, b, 1, warm, nf_aux, d_bars, nullptr, true, nullptr, h->stream, nullptr);
+            if (rc) return rc;
+        }
+        CUDA_TRY(cudaEventRecord(h->ev_comp[slot], h->stream));
+        CUDA_TRY(cudaStreamWaitEvent(h->s_d2h, h->ev_comp[slot], 0));
+        // next H2D into the other slot may start now; it must not overwrite this
+        // slot's pcm until this compute is done -> h2d stream waits on ev_comp of the slot it reuses
+        CUDA_TRY(cudaStreamWaitEvent(h->s_h2d, h->ev_comp[slot ^ 1], 0));
+        if (ne > 0) {
+            for (int ch = 0; ch < channels; ch++) {
+                size_t off_h = ((size_t)ch * nf_total + (size_t)(ea - fb)) * B;
+                size_t off_d = (size_t)ch * ne * B;
+                CUDA_TRY(cudaMemcpyAsync(bars + off_h, (float*)h->d_stage[slot][1] + off_d, sizeof(float) * ne * B, cudaMemcpyDeviceToHost, h->s_d2h));
+                if (bars_i32)
+                    CUDA_TRY(cudaMemcpyAsync(bars_i32 + off_h, (int32_t*)h->d_stage[slot][2] + off_d, sizeof(int32_t) * ne * B, cudaMemcpyDeviceToHost, h->s_d2h));
+                if (beat)
+                    CUDA_TRY(cudaMemcpyAsync(beat + (size_t)ch * nf_total + (ea - fb), (fftl_beat*)h->d_stage[slot][3] + (size_t)ch * ne,
+                                             sizeof(fftl_beat) * ne, cudaMemcpyDeviceToHost, h->s_d2h));
+            }
+        }
+        CUDA_TRY(cudaEventRecord(h->ev_d2h[slot], h->s_d2h));
+    }
+    CUDA_TRY(cudaStreamSynchronize(h->s_d2h));
+    CUDA_TRY(cudaStreamSynchronize(h->stream));
+    CUDA_TRY(cudaStreamSynchronize(h->s_h2d));
+    return FFTL_OK;
+}
+
+extern "C" void* fftl_host_alloc(uint64_t bytes)
+{
+    void* p = nullptr;
+    cudaError_t e = cudaHostAlloc(&p, bytes, cudaHostAllocDefault);
+    if (e != cudaSuccess) {
+        set_error(FFTL_ERR_NOMEM, "cudaHostAlloc(%llu) failed: %s", (unsigned long long)bytes, cudaGetErrorString(e));
+        return nullptr;
+    }
+    return p;
+}
+extern "C" void fftl_host_free(void* p)
+{
+    if (p) cudaFreeHost(p);
+}
+
+// ------------------------------------------------------------------ synth
+static unsigned long long frac64(double x)
+{
+    const double two64 = 18446744073709551616.0;
+    if (x < 0) return 0ull - frac64(-x);
+    x -= floor(x);
+    return (unsigned long long)(x * two64);
+}
+
+extern "C" int fftl_synth_pcm_device(int16_t* pcm, int32_t channels, int64_t samples, int64_t cstride, int64_t first, float sample_rate,
+                                     uint32_t seed, void* cuda_stream)
+{
+    if (!pcm || channels < 1 || channels > 65535 || samples < 0 || !(sample_rate > 0)) return set_error(FFTL_ERR_ARG, "bad synth arguments");
+    if (samples == 0) return FFTL_OK;
+    const double fs = (double)sample_rate;
+    unsigned long long period = (unsigned long long)(10.0 * fs);
+    if (period == 0) period = 1;
+    const double T = (double)period / fs;
+    std::vector<SynthChannel> hc(channels);
+    for (int c = 0; c < channels; c++) {
+        double f0 = (c & 1) ? 20000.0 : 20.0, f1 = (c & 1) ? 20.0 : 20000.0;
+        hc[c].A = frac64(f0 / fs);
+        hc[c].B = frac64((f1 - f0) / (2.0 * T * fs * fs));
+        hc[c].tone_step = frac64(94.0 / fs);
+        hc[c].am_step = frac64(2.0 / fs);
+    }
+    cudaStream_t st = (cudaStream_t)cuda_stream;
+    SynthChannel* dc = nullptr;
+    CUDA_TRY(cudaMalloc(&dc, sizeof(SynthChannel) * channels));
+    cudaError_t e = cudaMemcpyAsync(dc, hc.data(), sizeof(SynthChannel) * channels, cudaMemcpyHostToDevice, st);
+    if (e == cudaSuccess) {
+        SynthParams sp;
+        sp.pcm = pcm;
+        sp.samples = samples;
+        sp.channel_stride = cstride;
+        sp.first_sample = first;
+        sp.period = period;
+        sp.seed = seed;
+        sp.channels = channels;
+        long long blocks = (samples + 255) / 256;
+        if (blocks > 148 * 16) blocks = 148 * 16;
+        synth_pcm_kernel<<<dim3((unsigned)blocks, (unsigned)channels), 256, 0, st>>>(sp, dc);
+        e = cudaGetLastError();
+    }
+    cudaError_t e2 = cudaStreamSynchronize(st); // hc / dc lifetimes
+    cudaFree(dc);
+    if (e != cudaSuccess) return set_error(FFTL_ERR_CUDA, "synth launch failed: %s", cudaGetErrorString(e));
+    if (e2 != cudaSuccess) return set_error(FFTL_ERR_CUDA, "synth failed: %s", cudaGetErrorString(e2));
+    return FFTL_OK;
+}
+
+// ================================================================== compat
+// Drop-in layer for the reference's single-frame API.  One global context,
+// not thread-safe, exactly like the reference's globals (fft_calculate.c:6-7,
+// beatDetector.c:14-28).
+extern "C" {
+float beatMovementPerSec = 0; // beatDetector.c:25
+int beatposition = 0;         // beatDetector.c:26
+float timeDelta = 0;          // beatDetector.c:27
+int direction;                // beatDetector.c:28
+// The application's tempo ring (settingsFile.c:83).  The reference writes into
+// it; if the host program defines it we mirror the ring there, otherwise the
+// library's device-resident ring is the only copy.
+extern int* bassBeatBuffer __attribute__((weak));
+}
+
+struct CompatPlan {
+    bool live;
+    int n;
+    fftwf_complex* in;
+    fftwf_complex* out;
+    float2* d_in;
+    float2* d_out;
+    float2* d_tw;
+};
+static CompatPlan g_plan = {false, 0, nullptr, nullptr, nullptr, nullptr, nullptr};
+static CompatPlan g_plan256 = {false, 0, nullptr, nullptr, nullptr, nullptr, nullptr};
+static int g_compat_n = 2048; // reference N, global.h:3
+static cudaStream_t g_cstream = nullptr;
+static CompatBeatState* g_beat_state = nullptr;
+static int g_beat_value = 0;
+static int64_t g_compat_launches = 0;
+
+extern "C" int fftl_set_n(int32_t n)
+{
+    if (!pow2(n) || n < 256 || n > 16384) return set_error(FFTL_ERR_ARG, "fftl_set_n(%d): need a power of two in 256..16384", n);
+    if (g_plan.live) return set_error(FFTL_ERR_STATE, "fftl_set_n while a plan is live; call cleanupfft first");
+    g_compat_n = n;
+    return FFTL_OK;
+}
+extern "C" int fftl_get_n(void) { return g_compat_n; }
+extern "C" int64_t fftl_compat_launch_count(void) { return g_compat_launches; }
+
+static int compat_stream()
+{
+    if (!g_cstream) CUDA_TRY(cudaStreamCreateWithFlags(&g_cstream, cudaStreamNonBlocking));
+    return FFTL_OK;
+}
+
+static int compat_beat_state()
+{
+    if (g_beat_state) return FFTL_OK;
+    if (compat_stream()) return FFTL_ERR_CUDA;
+    CUDA_TRY(cudaMalloc(&g_beat_state, sizeof(CompatBeatState)));
+    CUDA_TRY(cudaMemset(g_beat_state, 0, sizeof(CompatBeatState)));
+    return FFTL_OK;
+}
+
+extern "C" void fftl_compat_reset_beat(void)
+{
+    if (g_beat_state) cudaMemset(g_beat_state, 0, sizeof(CompatBeatState));
+    g_beat_value = 0;
+    beatMovementPerSec = 0;
+    beatposition = 0;
+    direction = 0;
+}
+
+static void plan_release(CompatPlan* p)
+{
+    if (p->d_in) cudaFree(p->d_in);
+    if (p->d_out) cudaFree(p->d_out);
+    if (p->d_tw) cudaFree(p->d_tw);
+    memset(p, 0, sizeof(*p));
+    cudaGetLastError();
+}
+
+static int plan_init(CompatPlan* p, int n, fftwf_complex* in, fftwf_complex* out)
+{
+    plan_release(p);
+    if (!in || !out) return set_error(FFTL_ERR_ARG, "initializefft: NULL buffer");
+    int ndev = fftl_device_count();
+    if (ndev < 1) return set_error(FFTL_ERR_CUDA, "no CUDA device (libfftlines_cuda has no CPU fallback)");
+    if (compat_stream()) return FFTL_ERR_CUDA;
+    std::vector<float2> tw;
+    fill_twiddles(tw, n);
+    CUDA_TRY(cudaMalloc(&p->d_in, sizeof(float2) * n));
+    CUDA_TRY(cudaMalloc(&p->d_out, sizeof(float2) * n));
+    CUDA_TRY(cudaMalloc(&p->d_tw, sizeof(float2) * n));
+    CUDA_TRY(cudaMemcpy(p->d_tw, tw.data(), sizeof(float2) * n, cudaMemcpyHostToDevice));
+    p->n = n;
+    p->in = in;   // the plan is bound to the caller's buffers (fft_calculate.c:24)
+    p->out = out;
+    p->live = true;
+    return FFTL_OK;
+}
+
+static int plan_execute(CompatPlan* p)
+{
+    if (!p->live) return set_error(FFTL_ERR_STATE, "executefft before initializefft (the reference would dereference a NULL plan)");
+    // fft_calculate.c:29: the arguments are ignored, the bound buffers are used
+    CUDA_TRY(cudaMemcpyAsync(p->d_in, p->in, sizeof(float2) * p->n, cudaMemcpyHostToDevice, g_cstream));
+    CUDA_TRY(dispatch_c2c(p->n, p->d_in, p->d_out, p->d_tw, g_cstream));
+    g_compat_launches++;
+    CUDA_TRY(cudaMemcpyAsync(p->out, p->d_out, sizeof(float2) * p->n, cudaMemcpyDeviceToHost, g_cstream));
+    CUDA_TRY(cudaStreamSynchronize(g_cstream));
+    return FFTL_OK;
+}
+
+extern "C" void initializefft(fftwf_complex* in, fftwf_complex* out) { plan_init(&g_plan, g_compat_n, in, out); }
+extern "C" void executefft(fftwf_complex* in, fftwf_complex* out)
+{
+    (void)in;
+    (void)out;
+    plan_execute(&g_plan);
+}
+extern "C" void cleanupfft(void) { plan_release(&g_plan); }
+extern "C" void initializefft256(fftwf_complex* in, fftwf_complex* out) { plan_init(&g_plan256, FFTL_TEMPO_RING, in, out); }
+extern "C" void executefft256(fftwf_complex* in, fftwf_complex* out)
+{
+    (void)in;
+    (void)out;
+    plan_execute(&g_plan256);
+}
+extern "C" void cleanupfft256(void) { plan_release(&g_plan256); }
+
+static int add_beat_sample_impl(int w)
+{
+    if (fftl_device_count() < 1) return set_error(FFTL_ERR_CUDA, "no CUDA device (libfftlines_cuda has no CPU fallback)");
+    if (compat_beat_state()) return FFTL_ERR_CUDA;
+    compat_add_beat_sample_kernel<<<1, 32, 0, g_cstream>>>(g_beat_state, w);
+    CUDA_TRY(cudaGetLastError());
+    g_compat_launches++;
+    CUDA_TRY(cudaMemcpyAsync(&g_beat_value, &g_beat_state->beat_value, sizeof(int), cudaMemcpyDeviceToHost, g_cstream));
+    CUDA_TRY(cudaStreamSynchronize(g_cstream));
+    return FFTL_OK;
+}
+extern "C" void AddBeatSample(int weightedAverage) { add_beat_sample_impl(weightedAverage); }
+extern "C" int GetBeatValue(void) { return g_beat_value; }
+
+static int bass_beat_impl(fftwf_complex* output, fftwf_complex* beatinput, fftwf_complex* beatoutput)
+{
+    if (!output) return set_error(FFTL_ERR_ARG, "BassBeatDetector: output is NULL");
+    if (fftl_device_count() < 1) return set_error(FFTL_ERR_CUDA, "no CUDA device (libfftlines_cuda has no CPU fallback)");
+    if (!g_plan256.live) return set_error(FFTL_ERR_STATE, "BassBeatDetector before initializefft256");
+    if (compat_beat_state()) return FFTL_ERR_CUDA;
+    // beatDetector.c:105: N * timeDelta, left to right in float
+    float n_dt = (float)g_compat_n * timeDelta;
+    compat_bass_beat_kernel<<<1, 32, 0, g_cstream>>>(g_beat_state, output[4][REAL], output[4][IMAG], n_dt, g_plan256.d_tw, 1);
+    CUDA_TRY(cudaGetLastError());
+    g_compat_launches++;
+    static CompatBeatState host_copy; // 6 KB; the drop-in API is single-threaded like the reference
+    CUDA_TRY(cudaMemcpyAsync(&host_copy, g_beat_state, sizeof(CompatBeatState), cudaMemcpyDeviceToHost, g_cstream));
+    CUDA_TRY(cudaStreamSynchronize(g_cstream));
+    beatMovementPerSec = host_copy.movement_per_sec;
+    // the reference runs plan256, which is bound to the buffers given to
+    // initializefft256 (beatDetector.c:61-67 fill `beatinput`, the plan writes its own out)
+    if (beatinput) memcpy(beatinput, host_copy.beat_in, sizeof(float2) * FFTL_TEMPO_RING);
+    if (g_plan256.out) memcpy(g_plan256.out, host_copy.beat_out, sizeof(float2) * FFTL_TEMPO_RING);
+    if (beatoutput && (void*)beatoutput != (void*)g_plan256.out) memcpy(beatoutput, host_copy.beat_out, sizeof(float2) * FFTL_TEMPO_RING);
+    if (&bassBeatBuffer && bassBeatBuffer) memcpy(bassBeatBuffer, host_copy.tempo_ring, sizeof(int) * FFTL_TEMPO_RING);
+    return FFTL_OK;
+}
+extern "C" void BassBeatDetector(fftwf_complex* input, fftwf_complex* output, fftwf_complex* beatinput, fftwf_complex* beatoutput)
+{
+    (void)input; // unused by the reference as well
+    bass_beat_impl(output, beatinput, beatoutput);
+}

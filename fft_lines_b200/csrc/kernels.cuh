@@ -1,0 +1,478 @@
+// kernels.cuh -- device kernels of libfftlines_cuda (sm_100a).
+//
+//   stft_bars_kernel   the fused per-frame chain of the reference's WM_TIMER
+//                      (fft_lines/fft_lines.c:190-231, :281 first half):
+//                      int16 load (+window) -> FFT -> |.| -> bins -> SG ->
+//                      zoom -> float / int heights, band energy w and the
+//                      bass-bin magnitude.  Two real frames share one complex
+//                      transform (the reference wastes the imaginary half on
+//                      zeros, fft_lines.c:193).
+//   beat_post_kernel   the cross-frame part: AddBeatSample
+//                      (beatDetector.c:30-44) and BassBeatDetector
+//                      (beatDetector.c:51-106) for every frame in parallel.
+//   c2c_kernel         executefft / executefft256 (fft_calculate.c:27-30,43-46).
+//   compat_* kernels   single-call state updates for the drop-in beat API.
+//   synth_pcm_kernel   deterministic synthetic PCM.
+#pragma once
+#include <stdint.h>
+#include <limits.h>
+#include "fft_device.cuh"
+#include "../../include/fftlines.h"
+
+namespace fftl {
+
+// The reference's (int) casts compile to cvttss2si / cvttsd2si, which return
+// INT32_MIN ("integer indefinite") for NaN and out-of-range inputs.
+__device__ __forceinline__ int trunc_i32(float x, int strict)
+{
+    if (strict && (x != x || x >= 2147483648.0f)) return INT_MIN;
+    return __float2int_rz(x); // saturating, NaN -> 0
+}
+__device__ __forceinline__ int trunc_i32(double x, int strict)
+{
+    if (strict && (x != x || x >= 2147483648.0)) return INT_MIN;
+    return __double2int_rz(x);
+}
+__device__ __forceinline__ int wrap_add(int a, int b) { return (int)((unsigned)a + (unsigned)b); }
+__device__ __forceinline__ int wrap_sub(int a, int b) { return (int)((unsigned)a - (unsigned)b); }
+
+struct StftParams {
+    const int16_t* pcm;
+    long long channel_stride, sample_stride;
+    long long frame0;      // first frame computed (beat warm-up start)
+    long long frame_emit;  // first frame whose bars are written
+    long long frame_end;
+    long long nf_emit;     // frame_end - frame_emit   (output stride per channel)
+    long long nf_aux;      // aux stride per channel
+    long long aux_base;    // aux index of frame0 is (frame0 - aux_base)
+    const float* window;   // n floats or nullptr (RECT)
+    const float2* tw;      // W_n^m
+    const int* lo;
+    const int* hi;
+    const float* sg;       // (2w+1)^2 or nullptr
+    float* bars;
+    int* bars_i32;
+    int* aux_w;
+    int* aux_bass;
+    int hop, bars_n, sg_half, strict, bass_bin;
+    int beat_bars[4];
+    float zoom, circle_add;
+};
+
+template <int N> struct StftShape {
+    static constexpr int VPT = (N >= 16384) ? 32 : 16;
+    static constexpr int G = N / VPT;                       // threads per frame pair
+    static constexpr int PAIRS = (G >= 256) ? 1 : (256 / G > 8 ? 8 : 256 / G);
+    static constexpr int THREADS = G * PAIRS;
+    static size_t smem_bytes(int bars)
+    {
+        return (size_t)PAIRS * (padded_size(N) * sizeof(float2) + 2 * (size_t)bars * sizeof(float) + 8 * sizeof(int));
+    }
+};
+
+template <int N>
+__global__ void __launch_bounds__(StftShape<N>::THREADS) stft_bars_kernel(const StftParams p)
+{
+    using Sh = StftShape<N>;
+    constexpr int VPT = Sh::VPT, G = Sh::G, PAIRS = Sh::PAIRS;
+    extern __shared__ float2 smem[];
+    const int pic = threadIdx.x / G, g = threadIdx.x % G;
+    const int B = p.bars_n;
+    float2* s = smem + pic * padded_size(N);
+    float* raw = reinterpret_cast<float*>(smem + PAIRS * padded_size(N)) + pic * 2 * B; // [2][B]
+    int* beat_h = reinterpret_cast<int*>(reinterpret_cast<float*>(smem + PAIRS * padded_size(N)) + PAIRS * 2 * B) + pic * 8;
+    auto sync = [] { __syncthreads(); };
+
+    const long long pair = (long long)blockIdx.x * PAIRS + pic;
+    const int ch = blockIdx.y;
+    const long long fa = p.frame0 + 2 * pair;
+    const bool va = fa < p.frame_end, vb = fa + 1 < p.frame_end;
+    const int16_t* xa = p.pcm + ch * p.channel_stride + fa * p.hop * p.sample_stride;
+    const long long ss = p.sample_stride;
+    const long long hs = (long long)p.hop * ss;
+
+    // ---- load: z[i] = frame_a[i] + i*frame_b[i]  (fft_lines.c:190-194, imag reused)
+    float2 v[VPT];
+#pragma unroll
+    for (int t = 0; t < VPT / 16; t++) {
+#pragma unroll
+        for (int r = 0; r < 16; r++) {
+            int i = (g + t * G) + r * (N / 16);
+            float a = va ? (float)xa[i * ss] : 0.0f;
+            float b = vb ? (float)xa[i * ss + hs] : 0.0f;
+            if (p.window) {
+                float w = __ldg(p.window + i);
+                a *= w;
+                b *= w;
+            }
+            v[t * 16 + r] = make_float2(a, b);
+        }
+    }
+    fft_from_regs<N, G>(v, s, p.tw, g, sync);
+
+    // ---- untangle the two real spectra and take magnitudes (fft_lines.c:202)
+    for (int k = g; k <= N / 2; k += G) {
+        float2 z1 = s[pad_index(k)], z2 = s[pad_index((N - k) & (N - 1))];
+        float ar = z1.x + z2.x, ai = z1.y - z2.y; // 2 * Xa[k]
+        float br = z1.x - z2.x, bi = z1.y + z2.y; // 2i * Xb[k]
+        s[pad_index(k)] = make_float2(0.5f * sqrtf(fmaf(ar, ar, ai * ai)), 0.5f * sqrtf(fmaf(br, br, bi * bi)));
+    }
+    __syncthreads();
+
+    // ---- bins -> bars: mean of magnitudes over [lo,hi)  (identity in parity mode)
+    for (int b = g; b < B; b += G) {
+        int l = __ldg(p.lo + b), h = __ldg(p.hi + b);
+        float sa = 0.0f, sb = 0.0f;
+        for (int k = l; k < h; k++) {
+            float2 m = s[pad_index(k)];
+            sa += m.x;
+            sb += m.y;
+        }
+        float inv = 1.0f / (float)(h - l);
+        raw[b] = sa * inv;
+        raw[B + b] = sb * inv;
+    }
+    __syncthreads();
+
+    // ---- SG smoothing, zoom, (int) cast, outputs (fft_lines.c:202-207)
+    const int w = p.sg_half, m = 2 * w + 1;
+    const long long oa = (fa - p.frame_emit), ob = oa + 1;
+    const bool ea = va && fa >= p.frame_emit, eb = vb && fa + 1 >= p.frame_emit;
+    for (int b = g; b < B; b += G) {
+        float ya, yb;
+        if (w == 0) {
+            ya = raw[b];
+            yb = raw[B + b];
+        } else {
+            int row, base;
+            if (b < w) { row = b; base = 0; }
+            else if (b >= B - w) { row = m - (B - b); base = B - m; }
+            else { row = w; base = b - w; }
+            ya = 0.0f;
+            yb = 0.0f;
+            for (int k = 0; k < m; k++) {
+                float c = __ldg(p.sg + row * m + k);
+                ya = fmaf(c, raw[base + k], ya);
+                yb = fmaf(c, raw[B + base + k], yb);
+            }
+        }
+        float ha = ya * p.zoom, hb = yb * p.zoom;
+        int ia = trunc_i32(ha, p.strict), ib = trunc_i32(hb, p.strict);
+        if (p.circle_add != 0.0f) {
+            ha += p.circle_add;
+            hb += p.circle_add;
+            ia = wrap_add(ia, (int)p.circle_add);
+            ib = wrap_add(ib, (int)p.circle_add);
+        }
+        if (ea) {
+            long long o = ((long long)ch * p.nf_emit + oa) * B + b;
+            p.bars[o] = ha;
+            if (p.bars_i32) p.bars_i32[o] = ia;
+        }
+        if (eb) {
+            long long o = ((long long)ch * p.nf_emit + ob) * B + b;
+            p.bars[o] = hb;
+            if (p.bars_i32) p.bars_i32[o] = ib;
+        }
+#pragma unroll
+        for (int q = 0; q < 4; q++)
+            if (b == p.beat_bars[q]) {
+                beat_h[q] = ia;
+                beat_h[4 + q] = ib;
+            }
+    }
+    __syncthreads();
+
+    // ---- band energy w (fft_lines.c:281) and bass bin (beatDetector.c:53)
+    if (g < 2 && p.aux_w) {
+        bool valid = g == 0 ? va : vb;
+        if (valid) {
+            const int* h4 = beat_h + 4 * g;
+            int sum = wrap_add(wrap_add(h4[0], h4[1]), wrap_add(h4[2], h4[3]));
+            float2 mb = s[pad_index(p.bass_bin)];
+            long long o = (long long)ch * p.nf_aux + (fa + g - p.aux_base);
+            p.aux_w[o] = sum / 4;
+            p.aux_bass[o] = trunc_i32(g == 0 ? mb.x : mb.y, p.strict);
+        }
+    }
+}
+
+// --------------------------------------------------------------------------
+struct BeatParams {
+    const int* aux_w;
+    const int* aux_bass;
+    fftl_beat* out;        // [channels][nf_emit]
+    const float2* tw256;
+    long long aux_base, nf_aux, frame_emit, frame_end, nf_emit;
+    float n_times_dt;      // (float)N * timeDelta  (beatDetector.c:105)
+    int strict;
+};
+
+// Peak scan of beatDetector.c:78-103 done by one warp on hb[0..160].
+__device__ __forceinline__ int warp_peak_pick(const int* hb, int lane)
+{
+    int rank_base = 0;
+    int best_val = 0, best_idx = -1; // strict '>' against 0 start, lowest index wins ties
+    int first_peak = -1;
+#pragma unroll
+    for (int c = 0; c < FFTL_BEAT_SAMPLES / 32; c++) {
+        int i = lane + 32 * c;
+        int h = hb[i];
+        int dnew = wrap_sub(hb[i + 1], h);
+        int dold = (i == 0) ? 0 : wrap_sub(h, hb[i - 1]);
+        bool pk = (dold >= 0) && (dnew <= 0);
+        unsigned mask = __ballot_sync(0xffffffffu, pk);
+        int rank = rank_base + __popc(mask & ((1u << lane) - 1u));
+        if (first_peak < 0 && mask) first_peak = 32 * c + __ffs(mask) - 1;
+        if (pk && rank < 30 && i > 30 && h > best_val) {
+            best_val = h;
+            best_idx = i;
+        }
+        rank_base += __popc(mask);
+    }
+    // argmax over lanes: larger value wins, then smaller index
+#pragma unroll
+    for (int o = 16; o > 0; o >>= 1) {
+        int ov = __shfl_xor_sync(0xffffffffu, best_val, o);
+        int oi = __shfl_xor_sync(0xffffffffu, best_idx, o);
+        bool take = (oi >= 0) && (best_idx < 0 || ov > best_val || (ov == best_val && oi < best_idx));
+        if (take) {
+            best_val = ov;
+            best_idx = oi;
+        }
+    }
+    if (best_idx >= 0) return best_idx;
+    return first_peak >= 0 ? first_peak : 0;
+}
+
+constexpr int BEAT_FRAMES_PER_CTA = 16;
+constexpr int HB_STRIDE = FFTL_BEAT_SAMPLES + 2;
+
+__global__ void __launch_bounds__(256) beat_post_kernel(const BeatParams p)
+{
+    __shared__ float2 sf[BEAT_FRAMES_PER_CTA][padded_size(FFTL_TEMPO_RING)];
+    __shared__ int hbs[BEAT_FRAMES_PER_CTA][HB_STRIDE];
+    const int grp = threadIdx.x >> 4, g = threadIdx.x & 15;
+    const int ch = blockIdx.y;
+    const long long f = p.frame_emit + (long long)blockIdx.x * BEAT_FRAMES_PER_CTA + grp;
+    const bool valid = f < p.frame_end;
+    const int* bass = p.aux_bass + (long long)ch * p.nf_aux;
+    const int* wv = p.aux_w + (long long)ch * p.nf_aux;
+    auto sync = [] { __syncthreads(); };
+
+    // ring in ring order: slot i holds the newest frame j <= f with j % 256 == i
+    // (beatDetector.c:53-65; the ring starts zeroed, settingsFile.c:295-301)
+    float2 v[16];
+#pragma unroll
+    for (int r = 0; r < 16; r++) {
+        int i = g + 16 * r;
+        long long j = f - (long long)((unsigned)(f - i) & (FFTL_TEMPO_RING - 1));
+        int val = (valid && j >= 0) ? __ldg(bass + (j - p.aux_base)) : 0;
+        v[r] = make_float2((float)val, 0.0f);
+    }
+    float2* s = sf[grp];
+    stockham_pass<256, 16, 1, 16, false>(v, s, p.tw256, g, sync);
+    stockham_pass<256, 16, 16, 16, true>(v, s, p.tw256, g, sync);
+    // heightBuffer (beatDetector.c:69-75) plus the [160] the reference reads out of bounds
+    for (int i = g; i <= FFTL_BEAT_SAMPLES; i += 16) {
+        float2 z = s[pad_index(i)];
+        hbs[grp][i] = trunc_i32(sqrtf(fmaf(z.x, z.x, z.y * z.y)), p.strict);
+    }
+    __syncthreads();
+
+    const int warp = threadIdx.x >> 5, lane = threadIdx.x & 31;
+#pragma unroll
+    for (int q = 0; q < 2; q++) {
+        const int fr = 2 * warp + q;
+        const long long ff = p.frame_emit + (long long)blockIdx.x * BEAT_FRAMES_PER_CTA + fr;
+        if (ff >= p.frame_end) continue; // uniform per warp
+        int peak = warp_peak_pick(hbs[fr], lane);
+        // AddBeatSample: sum of the last 160 band energies (ring starts zeroed)
+        int part = 0;
+#pragma unroll
+        for (int c = 0; c < FFTL_BEAT_SAMPLES / 32; c++) {
+            long long j = ff - (lane + 32 * c);
+            if (j >= 0) part = wrap_add(part, __ldg(wv + (j - p.aux_base)));
+        }
+#pragma unroll
+        for (int o = 16; o > 0; o >>= 1) part = wrap_add(part, __shfl_xor_sync(0xffffffffu, part, o));
+        if (lane == 0) {
+            int wcur = __ldg(wv + (ff - p.aux_base));
+            int thr = part / FFTL_BEAT_SAMPLES;                 // beatDetector.c:41
+            float qv = __fdiv_rn((float)wcur, (float)thr);      // IEEE: x/0 = inf, 0/0 = NaN
+            int bv = trunc_i32(__fmul_rn(qv, 128.0f), 1);       // beatDetector.c:43 (always x86 semantics)
+            fftl_beat rec;
+            rec.w = wcur;
+            rec.thr = thr;
+            rec.beat_value = bv;
+            rec.flag = (thr > 0 && wcur > thr) ? 1 : 0;
+            rec.bass = __ldg(bass + (ff - p.aux_base));
+            rec.peak_index = peak;
+            rec.movement_per_sec = __fmul_rn(p.n_times_dt, (float)peak); // beatDetector.c:105
+            rec.reserved = 0;
+            p.out[(long long)ch * p.nf_emit + (ff - p.frame_emit)] = rec;
+        }
+    }
+}
+
+// --------------------------------------------------------------------------
+// executefft / executefft256: one complex transform, global -> global.
+template <int N>
+__global__ void __launch_bounds__(N / ((N >= 16384) ? 32 : 16)) c2c_kernel(const float2* __restrict__ in, float2* __restrict__ out,
+                                                                           const float2* __restrict__ tw)
+{
+    constexpr int VPT = (N >= 16384) ? 32 : 16, G = N / VPT;
+    extern __shared__ float2 smem[];
+    const int g = threadIdx.x;
+    auto sync = [] { __syncthreads(); };
+    float2 v[VPT];
+#pragma unroll
+    for (int t = 0; t < VPT / 16; t++)
+#pragma unroll
+        for (int r = 0; r < 16; r++) v[t * 16 + r] = in[(g + t * G) + r * (N / 16)];
+    fft_from_regs<N, G>(v, smem, tw, g, sync);
+    for (int k = g; k < N; k += G) out[k] = smem[pad_index(k)];
+}
+
+// --------------------------------------------------------------------------
+// Drop-in beat state (beatDetector.c:14-28) kept on the device.
+struct CompatBeatState {
+    int ring[FFTL_BEAT_SAMPLES];
+    int pos, sum, thr, beat_value;
+    int tempo_ring[FFTL_TEMPO_RING];
+    int tempo_pos;
+    int peak_index;
+    float movement_per_sec;
+    float2 beat_in[FFTL_TEMPO_RING];  // what the reference leaves in beatinput
+    float2 beat_out[FFTL_TEMPO_RING]; // ... and beatoutput
+};
+
+__global__ void compat_add_beat_sample_kernel(CompatBeatState* st, int w)
+{
+    if (threadIdx.x != 0) return;
+    // beatDetector.c:32-43
+    st->sum = wrap_sub(wrap_add(st->sum, w), st->ring[st->pos]);
+    st->ring[st->pos] = w;
+    st->pos = (st->pos + 1 == FFTL_BEAT_SAMPLES) ? 0 : st->pos + 1;
+    st->thr = st->sum / FFTL_BEAT_SAMPLES;
+    float q = __fdiv_rn((float)w, (float)st->thr);
+    st->beat_value = trunc_i32(__fmul_rn(q, 128.0f), 1);
+}
+
+// BassBeatDetector (beatDetector.c:51-106) for one call: one warp; lanes 0..15
+// run the 256-point transform, all 32 lanes run the peak scan.
+__global__ void __launch_bounds__(32) compat_bass_beat_kernel(CompatBeatState* st, float re, float im, float n_times_dt,
+                                                              const float2* __restrict__ tw256, int strict)
+{
+    __shared__ float2 s[padded_size(FFTL_TEMPO_RING)];
+    __shared__ int hb[HB_STRIDE];
+    const int lane = threadIdx.x;
+    if (lane == 0) {
+        double r = (double)re, i = (double)im;
+        st->tempo_ring[st->tempo_pos] = trunc_i32(sqrt(r * r + i * i), strict);          // :53
+        st->tempo_pos = (st->tempo_pos + 1 >= FFTL_TEMPO_RING) ? 0 : st->tempo_pos + 1;  // :54-59
+    }
+    __syncwarp();
+    if (lane < 16) {
+        auto sync16 = [] { __syncwarp(0x0000ffffu); };
+        float2 v[16];
+#pragma unroll
+        for (int r = 0; r < 16; r++) {
+            v[r] = make_float2((float)st->tempo_ring[lane + 16 * r], 0.0f);              // :61-65
+            st->beat_in[lane + 16 * r] = v[r];
+        }
+        stockham_pass<256, 16, 1, 16, false>(v, s, tw256, lane, sync16);                 // :67
+        stockham_pass<256, 16, 16, 16, true>(v, s, tw256, lane, sync16);
+    }
+    __syncwarp();
+    for (int i = lane; i < FFTL_TEMPO_RING; i += 32) st->beat_out[i] = s[pad_index(i)];
+    for (int i = lane; i <= FFTL_BEAT_SAMPLES; i += 32) {
+        float2 z = s[pad_index(i)];
+        double r = (double)z.x, q = (double)z.y;
+        hb[i] = trunc_i32(sqrt(r * r + q * q), strict);                                  // :69-75
+    }
+    __syncwarp();
+    int peak = warp_peak_pick(hb, lane);                                                 // :78-103
+    if (lane == 0) {
+        st->peak_index = peak;
+        st->movement_per_sec = __fmul_rn(n_times_dt, (float)peak);                       // :105
+    }
+}
+
+// --------------------------------------------------------------------------
+// Deterministic synthetic PCM; bit-identical to oracle/fftl_oracle.c
+// orc_synth_pcm (integer phase arithmetic + explicitly rounded double ops).
+struct SynthChannel {
+    unsigned long long A, B, tone_step, am_step;
+};
+struct SynthParams {
+    int16_t* pcm;
+    long long samples, channel_stride, first_sample;
+    unsigned long long period;
+    unsigned seed;
+    int channels;
+};
+
+__device__ __forceinline__ double sin_turns_u32(unsigned p)
+{
+    unsigned q = p >> 30;
+    unsigned r = p & 0x3FFFFFFFu;
+    if (q & 1u) r = 0x40000000u - r;
+    double x = __dmul_rn((double)r, 1.5707963267948966 / 1073741824.0);
+    double x2 = __dmul_rn(x, x);
+    double s = -7.6471637318198164759e-13;
+    s = __fma_rn(s, x2, 1.6059043836821614599e-10);
+    s = __fma_rn(s, x2, -2.5052108385441718775e-08);
+    s = __fma_rn(s, x2, 2.7557319223985890653e-06);
+    s = __fma_rn(s, x2, -1.9841269841269841270e-04);
+    s = __fma_rn(s, x2, 8.3333333333333333333e-03);
+    s = __fma_rn(s, x2, -1.6666666666666666667e-01);
+    s = __fma_rn(__dmul_rn(s, x2), x, x);
+    return (q & 2u) ? -s : s;
+}
+
+__device__ __forceinline__ void philox4x32_10(unsigned c0, unsigned c1, unsigned c2, unsigned c3, unsigned k0, unsigned k1,
+                                              unsigned* out)
+{
+#pragma unroll
+    for (int r = 0; r < 10; r++) {
+        unsigned hi0 = __umulhi(0xD2511F53u, c0), lo0 = 0xD2511F53u * c0;
+        unsigned hi1 = __umulhi(0xCD9E8D57u, c2), lo1 = 0xCD9E8D57u * c2;
+        unsigned n0 = hi1 ^ c1 ^ k0, n1 = lo1, n2 = hi0 ^ c3 ^ k1, n3 = lo0;
+        c0 = n0; c1 = n1; c2 = n2; c3 = n3;
+        k0 += 0x9E3779B9u;
+        k1 += 0xBB67AE85u;
+    }
+    out[0] = c0; out[1] = c1; out[2] = c2; out[3] = c3;
+}
+
+__global__ void __launch_bounds__(256) synth_pcm_kernel(const SynthParams p, const SynthChannel* __restrict__ chans)
+{
+    const int c = blockIdx.y;
+    const SynthChannel sc = chans[c];
+    for (long long i = (long long)blockIdx.x * blockDim.x + threadIdx.x; i < p.samples; i += (long long)gridDim.x * blockDim.x) {
+        unsigned long long n = (unsigned long long)(p.first_sample + i);
+        unsigned long long m = n % p.period;
+        unsigned long long ph = sc.A * m + sc.B * m * m + ((unsigned long long)c << 62);
+        double v = __dmul_rn(8000.0, sin_turns_u32((unsigned)(ph >> 32)));
+        if (c == 0) {
+            double tone = sin_turns_u32((unsigned)((sc.tone_step * n) >> 32));
+            double am = __dadd_rn(0.5, __dmul_rn(0.5, sin_turns_u32((unsigned)((sc.am_step * n) >> 32))));
+            double t = __dmul_rn(6000.0, am);
+            v = __dadd_rn(v, __dmul_rn(t, tone));
+        }
+        unsigned r[4];
+        philox4x32_10((unsigned)n, (unsigned)(n >> 32), 0u, 0u, p.seed + (unsigned)c, 0x5EED0000u, r);
+        int acc = 0;
+#pragma unroll
+        for (int k = 0; k < 4; k++) acc += (int)(r[k] & 0xFFFFu) + (int)(r[k] >> 16);
+        acc -= 262140;
+        int noise = (acc * 2449) >> 16;
+        v = __dadd_rn(v, (double)noise);
+        double rr = rint(v);
+        rr = fmin(fmax(rr, -32768.0), 32767.0);
+        p.pcm[(long long)c * p.channel_stride + i] = (int16_t)(int)rr;
+    }
+}
+
+} // namespace fftl

@@ -1,0 +1,46 @@
+"""Frame-range sharding of one STFT job across GPUs.
+
+Frames are independent up to the bar heights, and the beat stages need only the
+previous 255 frames' two integers, which ``fftl_stft_run*`` recomputes itself
+for any ``frame_begin``.  So a shard is just a ``[begin, end)`` frame range: no
+data-path collective, only an optional final gather of the outputs.
+"""
+
+
+def shard_frames(total_frames, world_size, rank):
+    """Contiguous, balanced split: the first ``total % world`` ranks get one more frame."""
+    if world_size < 1 or not (0 <= rank < world_size):
+        raise ValueError("bad world_size/rank")
+    base, extra = divmod(int(total_frames), world_size)
+    begin = rank * base + min(rank, extra)
+    end = begin + base + (1 if rank < extra else 0)
+    return begin, end
+
+
+def sample_span(frame_begin, frame_end, n, hop, warmup_frames=255):
+    """Samples a shard must hold: its frames plus the beat warm-up halo before it."""
+    if frame_end <= frame_begin:
+        return 0, 0
+    first = max(0, frame_begin - warmup_frames)
+    return first * hop, (frame_end - 1) * hop + n
+
+
+def gather_frames(local, total_frames, group=None, dst=None):
+    """All-gather (or gather to ``dst``) per-rank ``[channels, frames_r, ...]`` tensors along
+    the frame axis with torch.distributed.  Works on CPU (gloo) and GPU (nccl) tensors.
+    Returns the full tensor (on ``dst`` only when given, else on every rank)."""
+    import torch
+    import torch.distributed as dist
+    world = dist.get_world_size(group)
+    rank = dist.get_rank(group)
+    sizes = [shard_frames(total_frames, world, r) for r in range(world)]
+    parts = []
+    for r, (b, e) in enumerate(sizes):
+        shape = list(local.shape)
+        shape[1] = e - b
+        parts.append(torch.empty(shape, dtype=local.dtype, device=local.device))
+    if dst is None:
+        dist.all_gather(parts, local.contiguous(), group=group)
+        return torch.cat(parts, dim=1)
+    dist.gather(local.contiguous(), parts if rank == dst else None, dst=dst, group=group)
+    return torch.cat(parts, dim=1) if rank == dst else None

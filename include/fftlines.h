@@ -135,10 +135,11 @@ int fftl_stft_run(fftl_stft* h, const int16_t* pcm_host, int32_t channels,
 
 /* Number of kernel launches issued by this handle since creation. */
 int64_t fftl_stft_launch_count(const fftl_stft* h);
-/* Device time (ms, CUDA events on the launching stream) of the last
- * fftl_stft_run_device: whole call, and the dominant stft_bars kernel(s) only.
- * Forces a stream sync. */
-int fftl_stft_last_timing(fftl_stft* h, float* total_ms, float* bars_kernel_ms);
+/* Device time (ms, CUDA events recorded on the launching stream) summed over
+ * the fftl_stft_run_device calls made since the previous fftl_stft_timing call
+ * (at most the last 64): whole call, and the dominant stft_bars kernel only.
+ * Waits for those calls to finish. */
+int fftl_stft_timing(fftl_stft* h, int32_t* calls, float* total_ms, float* bars_kernel_ms);
 
 /* Pinned host memory helpers. */
 void* fftl_host_alloc(uint64_t bytes);

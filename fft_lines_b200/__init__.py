@@ -14,10 +14,10 @@ There is no CPU fallback and nothing here imports ``oracle/``.
 from ._capi import (FftlConfig, FftlBeat, FftLinesError, WINDOW_RECT, WINDOW_HANN, BINNING_LINEAR,
                     BINNING_LOG, BEAT_SAMPLES, TEMPO_RING, LIB_PATH)
 from .stft import (BatchedSpectrum, reference_config, extended_config, build_bins, build_sg, BEAT_DTYPE,
-                   device_count, synth_pcm_device, PinnedArray)
+                   device_count, synth_pcm_device, PinnedArray, measure_fp32_peak)
 from . import fft_calculate, beat_detector, sharding
 
 __all__ = ["FftlConfig", "FftlBeat", "FftLinesError", "BatchedSpectrum", "reference_config",
            "extended_config", "build_bins", "build_sg", "BEAT_DTYPE", "device_count", "synth_pcm_device",
-           "PinnedArray", "fft_calculate", "beat_detector", "sharding", "WINDOW_RECT", "WINDOW_HANN",
+           "PinnedArray", "measure_fp32_peak", "fft_calculate", "beat_detector", "sharding", "WINDOW_RECT", "WINDOW_HANN",
            "BINNING_LINEAR", "BINNING_LOG", "BEAT_SAMPLES", "TEMPO_RING", "LIB_PATH"]

@@ -46,7 +46,7 @@ EXPORTED_FUNCTIONS = {
         "fftl_config_reference", "fftl_config_extended", "fftl_config_validate", "fftl_build_bins",
         "fftl_build_sg", "fftl_stft_create", "fftl_stft_destroy", "fftl_stft_num_frames",
         "fftl_stft_run_device", "fftl_stft_run", "fftl_stft_launch_count", "fftl_stft_timing",
-        "fftl_host_alloc", "fftl_host_free", "fftl_synth_pcm_device", "fftl_last_error",
+        "fftl_host_alloc", "fftl_host_free", "fftl_synth_pcm_device", "fftl_measure_fp32_peak", "fftl_last_error",
         "fftl_last_error_string", "fftl_clear_error", "fftl_version", "fftl_device_count",
         "fftl_set_n", "fftl_get_n", "fftl_compat_reset_beat", "fftl_compat_launch_count",
     ],
@@ -73,7 +73,7 @@ def lib():
     if not os.path.exists(LIB_PATH):
         raise FileNotFoundError(
             "%s is missing: build it with `python -m fft_lines_b200.build` (there is no CPU fallback)" % LIB_PATH)
-    L = C.CDLL(LIB_PATH, mode=C.RTLD_GLOBAL)
+    L = C.CDLL(LIB_PATH)
     cfgp = C.POINTER(FftlConfig)
     i32p, f32p, i16p = C.POINTER(C.c_int32), C.POINTER(C.c_float), C.POINTER(C.c_int16)
     vp = C.c_void_p
@@ -100,6 +100,7 @@ def lib():
     L.fftl_host_free.argtypes = [vp]
     L.fftl_host_free.restype = None
     L.fftl_synth_pcm_device.argtypes = [vp, C.c_int32, C.c_int64, C.c_int64, C.c_int64, C.c_float, C.c_uint32, vp]
+    L.fftl_measure_fp32_peak.argtypes = [C.POINTER(C.c_double), C.c_int32]
     L.fftl_last_error_string.restype = C.c_char_p
     L.fftl_clear_error.restype = None
     L.fftl_set_n.argtypes = [C.c_int32]

@@ -402,7 +402,7 @@ extern "C" int64_t fftl_stft_launch_count(const fftl_stft* h) { return h ? h->la
 // Core: frames [fb, fe) of every channel; aux (w, bass) indexed from aux_base
 // with per-channel stride nf_aux.  `compute_from` <= fb is where this call
 // starts computing aux (frames before it must already be in the aux arrays).
-static int run_range(fftl_stft* h, const int16_t* pcm, int channels, int64_t cstride, int64_t sstride, int64_t compute_from,
+static int run_range(fftl_stft* h, const int16_t* pcm, int channels, int64_t cstride, int64_t sstride, int64_t frames_total, int64_t compute_from,
                      int64_t fb, int64_t fe, int64_t out_base, int64_t nf_emit, int64_t aux_base, int64_t nf_aux, float* bars,
                      int32_t* bars_i32, bool aux, fftl_beat* beat, cudaStream_t st, cudaEvent_t* evs)
 {
@@ -415,6 +415,7 @@ static int run_range(fftl_stft* h, const int16_t* pcm, int channels, int64_t cst
     p.frame0 = compute_from;
     p.frame_emit = fb;
     p.frame_end = fe;
+    p.frames_total = frames_total;
     p.nf_emit = nf_emit;
     p.nf_aux = nf_aux;
     p.aux_base = aux_base;
@@ -482,13 +483,13 @@ extern "C" int fftl_stft_run_device(fftl_stft* h, const int16_t* pcm, int32_t ch
     if (rc) return rc;
     if (fe == fb) return FFTL_OK;
     CUDA_TRY(cudaSetDevice(h->device));
-    cudaStream_t st = cuda_stream ? (cudaStream_t)cuda_stream : h->stream;
+    cudaStream_t st = (cudaStream_t)cuda_stream; // NULL = CUDA's default stream, as everywhere in CUDA
     int64_t warm = fb;
     if (beat) {
         warm = fb - (FFTL_TEMPO_RING - 1);
         if (warm < 0) warm = 0;
-        // keep frame pairs aligned to even offsets from `warm`
     }
+    warm &= ~(int64_t)1; // frame f always shares its transform with frame f^1: results do not depend on the shard start
     int64_t nf_aux = fe - warm;
     if (beat) {
         size_t need = sizeof(int) * 2 * (size_t)channels * (size_t)nf_aux;
@@ -501,7 +502,7 @@ extern "C" int fftl_stft_run_device(fftl_stft* h, const int16_t* pcm, int32_t ch
         }
     }
     cudaEvent_t* evs = h->ev[h->timing_next];
-    rc = run_range(h, pcm, channels, cstride, sstride, warm, fb, fe, fb, fe - fb, warm, nf_aux, bars, bars_i32, beat != nullptr, beat, st, evs);
+    rc = run_range(h, pcm, channels, cstride, sstride, fftl_stft_num_frames(h, samples), warm, fb, fe, fb, fe - fb, warm, nf_aux, bars, bars_i32, beat != nullptr, beat, st, evs);
     if (rc) return rc;
     h->timing_next = (h->timing_next + 1) % TIMING_SLOTS;
     if (h->timing_count < TIMING_SLOTS) h->timing_count++;
@@ -551,6 +552,7 @@ extern "C" int fftl_stft_run(fftl_stft* h, const int16_t* pcm, int32_t channels,
         warm = fb - (FFTL_TEMPO_RING - 1);
         if (warm < 0) warm = 0;
     }
+    warm &= ~(int64_t)1; // same pairing as the device path (chunks are even-sized)
     const int64_t nf_aux = fe - warm;
     if (beat) {
         size_t need = sizeof(int) * 2 * (size_t)channels * (size_t)nf_aux;
@@ -572,7 +574,11 @@ extern "C" int fftl_stft_run(fftl_stft* h, const int16_t* pcm, int32_t channels,
         int64_t b = a + chunk < fe ? a + chunk : fe; // compute frames [a,b)
         int64_t ea = a > fb ? a : fb;                // emit frames [ea,b)
         int64_t ne = b > ea ? b - ea : 0;
-        int64_t s0 = a * hop, s1 = (b - 1) * hop + n; // sample span per channel
+        // chunks are even-sized, so b is even unless it is fe: then frame b (if it exists) is the
+        // partner of b-1 and its samples are uploaded too
+        const int64_t F_all = fftl_stft_num_frames(h, samples);
+        int64_t avail = (b & 1) && b < F_all ? b + 1 : b;
+        int64_t s0 = a * hop, s1 = (avail - 1) * hop + n; // sample span per channel
         int64_t span = s1 - s0;
         size_t pcm_bytes = sizeof(int16_t) * (size_t)channels * span;
         size_t bars_bytes = sizeof(float) * (size_t)channels * (size_t)(ne > 0 ? ne : 1) * B;
@@ -602,9 +608,9 @@ extern "C" int fftl_stft_run(fftl_stft* h, const int16_t* pcm, int32_t channels,
             int32_t* d_i32 = bars_i32 ? (int32_t*)h->d_stage[slot][2] : nullptr;
             fftl_beat* d_beat = beat ? (fftl_beat*)h->d_stage[slot][3] : nullptr;
             if (ne > 0)
-                rc = run_range(h, base, channels, dcs, dss, a, ea, b, ea, ne, warm, nf_aux, d_bars, d_i32, beat != nullptr, d_beat, h->stream, nullptr);
+                rc = run_range(h, base, channels, dcs, dss, avail, a, ea, b, ea, ne, warm, nf_aux, d_bars, d_i32, beat != nullptr, d_beat, h->stream, nullptr);
             else // pure beat warm-up chunk: band energy / bass only, nothing emitted
-                rc = run_range(h, base, channels, dcs, dss, a, b, b, b, 1, warm, nf_aux, d_bars, nullptr, true, nullptr, h->stream, nullptr);
+                rc = run_range(h, base, channels, dcs, dss, avail, a, b, b, b, 1, warm, nf_aux, d_bars, nullptr, beat != nullptr, nullptr, h->stream, nullptr);
             if (rc) return rc;
         }
         CUDA_TRY(cudaEventRecord(h->ev_comp[slot], h->stream));
@@ -645,6 +651,44 @@ extern "C" void* fftl_host_alloc(uint64_t bytes)
 extern "C" void fftl_host_free(void* p)
 {
     if (p) cudaFreeHost(p);
+}
+
+// ------------------------------------------------------------------ probes
+// Dense FP32 FMA rate of the current device (2 flop per FMA), best of `reps`.
+extern "C" int fftl_measure_fp32_peak(double* tflops, int32_t reps)
+{
+    if (!tflops) return set_error(FFTL_ERR_ARG, "tflops is NULL");
+    int dev = 0, sms = 0;
+    CUDA_TRY(cudaGetDevice(&dev));
+    CUDA_TRY(cudaDeviceGetAttribute(&sms, cudaDevAttrMultiProcessorCount, dev));
+    float* d = nullptr;
+    CUDA_TRY(cudaMalloc(&d, 64));
+    cudaEvent_t e0, e1;
+    CUDA_TRY(cudaEventCreate(&e0));
+    CUDA_TRY(cudaEventCreate(&e1));
+    const int iters = 4096, blocks = sms * 8, threads = 256;
+    double best = 0;
+    if (reps < 1) reps = 1;
+    for (int r = 0; r < reps + 1; r++) {
+        cudaEventRecord(e0, 0);
+        fp32_peak_kernel<<<blocks, threads>>>(d, iters, 1.0000001f, 1e-9f);
+        cudaEventRecord(e1, 0);
+        cudaError_t e = cudaEventSynchronize(e1);
+        if (e != cudaSuccess) {
+            cudaFree(d);
+            return set_error(FFTL_ERR_CUDA, "fp32 probe failed: %s", cudaGetErrorString(e));
+        }
+        float ms = 0;
+        cudaEventElapsedTime(&ms, e0, e1);
+        double fl = 2.0 * 64.0 * (double)iters * (double)blocks * (double)threads;
+        double tf = fl / ((double)ms * 1e-3) / 1e12;
+        if (r > 0 && tf > best) best = tf; // first launch is the warm-up
+    }
+    cudaEventDestroy(e0);
+    cudaEventDestroy(e1);
+    cudaFree(d);
+    *tflops = best;
+    return FFTL_OK;
 }
 
 // ------------------------------------------------------------------ synth

@@ -34,13 +34,17 @@ def gather_frames(local, total_frames, group=None, dst=None):
     world = dist.get_world_size(group)
     rank = dist.get_rank(group)
     sizes = [shard_frames(total_frames, world, r) for r in range(world)]
-    parts = []
-    for r, (b, e) in enumerate(sizes):
-        shape = list(local.shape)
-        shape[1] = e - b
-        parts.append(torch.empty(shape, dtype=local.dtype, device=local.device))
+    # collectives need equal shapes: pad every shard to the largest (they differ by at most one frame)
+    fmax = max(e - b for b, e in sizes)
+    shape = list(local.shape)
+    shape[1] = fmax
+    padded = torch.zeros(shape, dtype=local.dtype, device=local.device)
+    padded[:, :local.shape[1]] = local
+    parts = [torch.empty(shape, dtype=local.dtype, device=local.device) for _ in range(world)]
     if dst is None:
-        dist.all_gather(parts, local.contiguous(), group=group)
-        return torch.cat(parts, dim=1)
-    dist.gather(local.contiguous(), parts if rank == dst else None, dst=dst, group=group)
-    return torch.cat(parts, dim=1) if rank == dst else None
+        dist.all_gather(parts, padded, group=group)
+    else:
+        dist.gather(padded, parts if rank == dst else None, dst=dst, group=group)
+        if rank != dst:
+            return None
+    return torch.cat([p[:, :e - b] for p, (b, e) in zip(parts, sizes)], dim=1)

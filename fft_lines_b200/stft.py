@@ -22,6 +22,13 @@ def device_count():
     return _capi.lib().fftl_device_count()
 
 
+def measure_fp32_peak(reps=5):
+    """Measured FP32 FMA rate of the current CUDA device in TFLOP/s."""
+    v = C.c_double()
+    _capi.check(_capi.lib().fftl_measure_fp32_peak(C.byref(v), reps))
+    return v.value
+
+
 def reference_config(n=2048, hop=512, bars=100, zoom=1e-4, sample_rate=48000.0, circle=0):
     """Parity mode: what the reference computes (RECT window, bar i = bin i, no smoothing)."""
     c = FftlConfig()

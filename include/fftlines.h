@@ -123,7 +123,7 @@ int fftl_stft_run_device(fftl_stft* h, const int16_t* pcm_dev, int32_t channels,
                          int64_t samples_per_channel, int64_t channel_stride,
                          int64_t sample_stride, int64_t frame_begin, int64_t frame_end,
                          float* bars_dev, int32_t* bars_i32_dev, fftl_beat* beat_dev,
-                         void* cuda_stream /* cudaStream_t or NULL = handle's stream */);
+                         void* cuda_stream /* cudaStream_t; NULL = CUDA's default stream */);
 
 /* Same, host buffers.  Copies are chunked by frame range and overlapped with
  * the kernels on three streams; buffers from fftl_host_alloc (pinned) make the
@@ -151,6 +151,10 @@ void  fftl_host_free(void* p);
 int fftl_synth_pcm_device(int16_t* pcm_dev, int32_t channels, int64_t samples,
                           int64_t channel_stride, int64_t first_sample,
                           float sample_rate, uint32_t seed, void* cuda_stream);
+
+/* Measured dense FP32 FMA rate (TFLOP/s, 2 flop per FMA) of the current device:
+ * the denominator of the compute roofline (not in MEASURED_PEAKS.json).      */
+int fftl_measure_fp32_peak(double* tflops, int32_t reps);
 
 /* ---- errors / info ----------------------------------------------------- */
 int         fftl_last_error(void);          /* sticky until fftl_clear_error */

@@ -13,6 +13,7 @@
 #include <vector>
 
 #include "kernels.cuh"
+#include "stft_rdif.cuh"
 #include "../../include/fft_calculate.h"
 #include "../../include/beatDetector.h"
 
@@ -265,6 +266,16 @@ struct fftl_stft {
     int* d_lo;
     int* d_hi;
     float* d_sg;
+    // fast path (stft_rdif.cuh): sub-transform twiddles and the balanced binning segments
+    float2* d_twm;
+    int* d_seg_bar;
+    int* d_seg_lo;
+    int* d_seg_hi;
+    int* d_bar_seg0;
+    float* d_bar_inv;
+    int nseg;
+    int num_sms;
+    int64_t fast_launches;
     int* d_aux;                     // [2][channels][nf_aux] (w then bass)
     size_t aux_capacity;            // ints
     int64_t launches;
@@ -348,6 +359,42 @@ extern "C" int fftl_stft_create(const fftl_config* cfg, int device, fftl_stft** 
         H_TRY(cudaMalloc(&h->d_sg, sizeof(float) * m * m));
         H_TRY(cudaMemcpy(h->d_sg, sg.data(), sizeof(float) * m * m, cudaMemcpyHostToDevice));
     }
+    {
+        // balanced binning: every bar is cut into segments of at most L bins (at most 8 per bar), so no
+        // lane ever walks a long bin range; partial sums are combined in a fixed order (deterministic)
+        int maxcnt = 1;
+        for (int b = 0; b < B; b++) maxcnt = hi[b] - lo[b] > maxcnt ? hi[b] - lo[b] : maxcnt;
+        int L = (maxcnt + 7) / 8;
+        if (L < 8) L = 8;
+        std::vector<int> seg_bar, seg_lo, seg_hi, bar_seg0(B + 1);
+        std::vector<float> bar_inv(B);
+        for (int b = 0; b < B; b++) {
+            bar_seg0[b] = (int)seg_lo.size();
+            for (int k = lo[b]; k < hi[b]; k += L) {
+                seg_bar.push_back(b);
+                seg_lo.push_back(k);
+                seg_hi.push_back(k + L < hi[b] ? k + L : hi[b]);
+            }
+            bar_inv[b] = 1.0f / (float)(hi[b] - lo[b]);
+        }
+        bar_seg0[B] = (int)seg_lo.size();
+        h->nseg = (int)seg_lo.size();
+        H_TRY(cudaMalloc(&h->d_seg_bar, sizeof(int) * h->nseg));
+        H_TRY(cudaMalloc(&h->d_seg_lo, sizeof(int) * h->nseg));
+        H_TRY(cudaMalloc(&h->d_seg_hi, sizeof(int) * h->nseg));
+        H_TRY(cudaMalloc(&h->d_bar_seg0, sizeof(int) * (B + 1)));
+        H_TRY(cudaMalloc(&h->d_bar_inv, sizeof(float) * B));
+        H_TRY(cudaMemcpy(h->d_seg_bar, seg_bar.data(), sizeof(int) * h->nseg, cudaMemcpyHostToDevice));
+        H_TRY(cudaMemcpy(h->d_seg_lo, seg_lo.data(), sizeof(int) * h->nseg, cudaMemcpyHostToDevice));
+        H_TRY(cudaMemcpy(h->d_seg_hi, seg_hi.data(), sizeof(int) * h->nseg, cudaMemcpyHostToDevice));
+        H_TRY(cudaMemcpy(h->d_bar_seg0, bar_seg0.data(), sizeof(int) * (B + 1), cudaMemcpyHostToDevice));
+        H_TRY(cudaMemcpy(h->d_bar_inv, bar_inv.data(), sizeof(float) * B, cudaMemcpyHostToDevice));
+        std::vector<float2> twm;
+        fill_twiddles(twm, n / 16);
+        H_TRY(cudaMalloc(&h->d_twm, sizeof(float2) * (n / 16)));
+        H_TRY(cudaMemcpy(h->d_twm, twm.data(), sizeof(float2) * (n / 16), cudaMemcpyHostToDevice));
+        H_TRY(cudaDeviceGetAttribute(&h->num_sms, cudaDevAttrMultiProcessorCount, device));
+    }
     for (int i = 0; i < TIMING_SLOTS; i++)
         for (int k = 0; k < 3; k++) H_TRY(cudaEventCreate(&h->ev[i][k]));
     for (int i = 0; i < 2; i++) {
@@ -374,6 +421,12 @@ extern "C" void fftl_stft_destroy(fftl_stft* h)
     cudaFree(h->d_hi);
     cudaFree(h->d_sg);
     cudaFree(h->d_aux);
+    cudaFree(h->d_twm);
+    cudaFree(h->d_seg_bar);
+    cudaFree(h->d_seg_lo);
+    cudaFree(h->d_seg_hi);
+    cudaFree(h->d_bar_seg0);
+    cudaFree(h->d_bar_inv);
     for (int i = 0; i < 2; i++)
         for (int k = 0; k < 4; k++) cudaFree(h->d_stage[i][k]);
     for (int i = 0; i < TIMING_SLOTS; i++)
@@ -399,10 +452,78 @@ extern "C" int64_t fftl_stft_num_frames(const fftl_stft* h, int64_t samples)
 
 extern "C" int64_t fftl_stft_launch_count(const fftl_stft* h) { return h ? h->launches : 0; }
 
+// Fast path (stft_rdif.cuh).  Returns cudaErrorNotSupported when the configuration is not covered.
+static const int RDIF_F = 4;
+template <int HOPQ, bool WIN> static cudaError_t launch_rdif(const fftl_stft* h, const RdifParams& p, cudaStream_t st)
+{
+    using Sh = RdifShape<4096, RDIF_F>;
+    size_t smem = Sh::smem_bytes(p.bars_n, p.nseg);
+    if (smem > 110 * 1024) return cudaErrorNotSupported; // two CTAs per SM is the design point
+    auto kern = stft_bars_rdif_kernel<4096, RDIF_F, HOPQ, WIN>;
+    cudaError_t e = cudaFuncSetAttribute(kern, cudaFuncAttributeMaxDynamicSharedMemorySize, (int)smem);
+    if (e != cudaSuccess) return e;
+    long long grid = 2ll * h->num_sms;
+    if (grid > p.total_tiles) grid = p.total_tiles;
+    kern<<<(unsigned)grid, Sh::THREADS, smem, st>>>(p);
+    return cudaGetLastError();
+}
+
+static cudaError_t try_rdif(const fftl_stft* h, const StftParams& q, int channels, long long samples, cudaStream_t st)
+{
+    const fftl_config& c = h->cfg;
+    if (c.n != 4096 || q.sample_stride != 1 || (c.hop % 256) != 0) return cudaErrorNotSupported;
+    const int hopq = c.hop / 256;
+    if (hopq != 1 && hopq != 2 && hopq != 4) return cudaErrorNotSupported;
+    if (getenv("FFTL_DISABLE_RDIF")) return cudaErrorNotSupported;
+    RdifParams p;
+    memset(&p, 0, sizeof(p));
+    p.pcm = q.pcm;
+    p.channel_stride = q.channel_stride;
+    p.samples = samples;
+    p.frame0 = q.frame0;
+    p.frame_emit = q.frame_emit;
+    p.frame_end = q.frame_end;
+    p.frames_total = q.frames_total;
+    p.nf_emit = q.nf_emit;
+    p.nf_aux = q.nf_aux;
+    p.aux_base = q.aux_base;
+    p.tiles_per_channel = (q.frame_end - q.frame0 + RDIF_F - 1) / RDIF_F;
+    p.total_tiles = p.tiles_per_channel * channels;
+    if (p.total_tiles <= 0) return cudaSuccess;
+    p.window = q.window;
+    p.tw = q.tw;
+    p.twm = h->d_twm;
+    p.seg_bar = h->d_seg_bar;
+    p.seg_lo = h->d_seg_lo;
+    p.seg_hi = h->d_seg_hi;
+    p.bar_seg0 = h->d_bar_seg0;
+    p.bar_inv = h->d_bar_inv;
+    p.sg = q.sg;
+    p.bars = q.bars;
+    p.bars_i32 = q.bars_i32;
+    p.aux_w = q.aux_w;
+    p.aux_bass = q.aux_bass;
+    p.hop = q.hop;
+    p.bars_n = q.bars_n;
+    p.nseg = h->nseg;
+    p.sg_half = q.sg_half;
+    p.strict = q.strict;
+    p.bass_bin = q.bass_bin;
+    for (int i = 0; i < 4; i++) p.beat_bars[i] = q.beat_bars[i];
+    p.zoom = q.zoom;
+    p.circle_add = q.circle_add;
+    const bool win = q.window != nullptr;
+    switch (hopq) {
+    case 1: return win ? launch_rdif<1, true>(h, p, st) : launch_rdif<1, false>(h, p, st);
+    case 2: return win ? launch_rdif<2, true>(h, p, st) : launch_rdif<2, false>(h, p, st);
+    default: return win ? launch_rdif<4, true>(h, p, st) : launch_rdif<4, false>(h, p, st);
+    }
+}
+
 // Core: frames [fb, fe) of every channel; aux (w, bass) indexed from aux_base
 // with per-channel stride nf_aux.  `compute_from` <= fb is where this call
 // starts computing aux (frames before it must already be in the aux arrays).
-static int run_range(fftl_stft* h, const int16_t* pcm, int channels, int64_t cstride, int64_t sstride, int64_t frames_total, int64_t compute_from,
+static int run_range(fftl_stft* h, const int16_t* pcm, int channels, int64_t cstride, int64_t sstride, int64_t samples, int64_t frames_total, int64_t compute_from,
                      int64_t fb, int64_t fe, int64_t out_base, int64_t nf_emit, int64_t aux_base, int64_t nf_aux, float* bars,
                      int32_t* bars_i32, bool aux, fftl_beat* beat, cudaStream_t st, cudaEvent_t* evs)
 {
@@ -439,7 +560,13 @@ static int run_range(fftl_stft* h, const int16_t* pcm, int channels, int64_t cst
     p.circle_add = c.circle ? 10.0f : 0.0f; // fft_lines.c:204-207
     long long pairs = (fe - compute_from + 1) / 2;
     if (evs) CUDA_TRY(cudaEventRecord(evs[0], st));
-    CUDA_TRY(dispatch_stft(c.n, p, channels, pairs, st));
+    cudaError_t fe_ = try_rdif(h, p, channels, samples, st);
+    if (fe_ == cudaErrorNotSupported) {
+        CUDA_TRY(dispatch_stft(c.n, p, channels, pairs, st)); // generic kernel: any n, strided PCM, any hop
+    } else {
+        CUDA_TRY(fe_);
+        h->fast_launches++;
+    }
     h->launches++;
     if (evs) CUDA_TRY(cudaEventRecord(evs[1], st));
     if (beat && fe > fb) {
@@ -502,7 +629,7 @@ extern "C" int fftl_stft_run_device(fftl_stft* h, const int16_t* pcm, int32_t ch
         }
     }
     cudaEvent_t* evs = h->ev[h->timing_next];
-    rc = run_range(h, pcm, channels, cstride, sstride, fftl_stft_num_frames(h, samples), warm, fb, fe, fb, fe - fb, warm, nf_aux, bars, bars_i32, beat != nullptr, beat, st, evs);
+    rc = run_range(h, pcm, channels, cstride, sstride, samples, fftl_stft_num_frames(h, samples), warm, fb, fe, fb, fe - fb, warm, nf_aux, bars, bars_i32, beat != nullptr, beat, st, evs);
     if (rc) return rc;
     h->timing_next = (h->timing_next + 1) % TIMING_SLOTS;
     if (h->timing_count < TIMING_SLOTS) h->timing_count++;
@@ -608,9 +735,9 @@ extern "C" int fftl_stft_run(fftl_stft* h, const int16_t* pcm, int32_t channels,
             int32_t* d_i32 = bars_i32 ? (int32_t*)h->d_stage[slot][2] : nullptr;
             fftl_beat* d_beat = beat ? (fftl_beat*)h->d_stage[slot][3] : nullptr;
             if (ne > 0)
-                rc = run_range(h, base, channels, dcs, dss, avail, a, ea, b, ea, ne, warm, nf_aux, d_bars, d_i32, beat != nullptr, d_beat, h->stream, nullptr);
+                rc = run_range(h, base, channels, dcs, dss, s1, avail, a, ea, b, ea, ne, warm, nf_aux, d_bars, d_i32, beat != nullptr, d_beat, h->stream, nullptr);
             else // pure beat warm-up chunk: band energy / bass only, nothing emitted
-                rc = run_range(h, base, channels, dcs, dss, avail, a, b, b, b, 1, warm, nf_aux, d_bars, nullptr, beat != nullptr, nullptr, h->stream, nullptr);
+                rc = run_range(h, base, channels, dcs, dss, s1, avail, a, b, b, b, 1, warm, nf_aux, d_bars, nullptr, beat != nullptr, nullptr, h->stream, nullptr);
             if (rc) return rc;
         }
         CUDA_TRY(cudaEventRecord(h->ev_comp[slot], h->stream));

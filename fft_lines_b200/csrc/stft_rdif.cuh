@@ -1,0 +1,308 @@
+// stft_rdif.cuh -- the fast path of the fused STFT->bars kernel (sm_100a).
+//
+// Real-input decimation-in-frequency transform of size N = 16*M, built so that
+// the FP32 pipe -- not shared-memory bandwidth -- is the limiter:
+//
+//   pass A  thread t (0..M-1) owns column t: the 16 samples x[t + M*q] of a frame.
+//           hop = HOPQ*M, so consecutive frames of the tile reuse the same
+//           registers (frame f uses xr[q + HOPQ*f]): every int16 sample is loaded
+//           and converted once per tile, not once per frame.
+//           Real 16-point DFT over q (66 flops, half of a complex one) gives
+//           Y_t[k0], k0 = 0..8; twiddle by W_N^(t*k0) (register-resident).
+//   pass B/C for each k0 a complex M-point FFT over t yields X[k0 + 16 m].
+//           k0 = 1..7 are full complex sub-transforms; k0 = 0 and k0 = 8 have real
+//           inputs, so frames f and f^1 share one complex sub-transform each
+//           (untangled with half-warp shuffles).  8 sub-transforms per frame.
+//           One sub-transform is done by M/16 lanes with warp-level syncs only.
+//   bins    magnitudes -> padded per-frame array -> balanced segment sums ->
+//           bars -> Savitzky-Golay -> zoom -> float/int heights, band energy.
+//
+// What the reference does per tick (fft_lines/fft_lines.c:190-208, :281) happens
+// here for a tile of F frames per CTA iteration; CTAs are persistent.
+// Shared memory per frame: 8 slots * M complex (+1/16 padding) + N/2+1 magnitudes.
+#pragma once
+#include "kernels.cuh"
+
+namespace fftl {
+
+struct RdifParams {
+    const int16_t* pcm;
+    long long channel_stride;   // sample_stride is 1 on this path
+    long long samples;          // samples per channel (loads beyond it read as 0)
+    long long frame0, frame_emit, frame_end, frames_total;
+    long long nf_emit, nf_aux, aux_base;
+    long long tiles_per_channel;
+    long long total_tiles;
+    const float* window;        // n floats (all ones for RECT)
+    const float2* tw;           // W_n^m
+    const float2* twm;          // W_M^m  (sub-transform twiddles)
+    const int* seg_bar;         // segment list for balanced binning
+    const int* seg_lo;
+    const int* seg_hi;
+    const int* bar_seg0;        // [bars+1] first segment of each bar
+    const float* bar_inv;       // 1 / (hi - lo)
+    const float* sg;
+    float* bars;
+    int* bars_i32;
+    int* aux_w;
+    int* aux_bass;
+    int hop, bars_n, nseg, sg_half, strict, bass_bin;
+    int beat_bars[4];
+    float zoom, circle_add;
+};
+
+// Real 16-point DFT: x[0..15] real -> Y[0..8] (Y[0], Y[8] real).  66 flops.
+// yr/yi are indexed by k0; yi[0] and yi[8] are not written.
+__device__ __forceinline__ void real_dft16(const float* x, float* yr, float* yi)
+{
+    float s[8], d[8];
+#pragma unroll
+    for (int q = 0; q < 8; q++) {
+        s[q] = x[q] + x[q + 8];
+        d[q] = x[q] - x[q + 8];
+    }
+    // even outputs: real 8-point DFT of s
+    float a0 = s[0] + s[4], a1 = s[1] + s[5], a2 = s[2] + s[6], a3 = s[3] + s[7];
+    float b0 = s[0] - s[4], b1 = s[1] - s[5], b2 = s[2] - s[6], b3 = s[3] - s[7];
+    float e0 = a0 + a2, e1 = a1 + a3;
+    yr[0] = e0 + e1;
+    yr[8] = e0 - e1;
+    yr[4] = a0 - a2;
+    yi[4] = -(a1 - a3);
+    float p = (b1 - b3) * FFTL_SQRT1_2, m = (b1 + b3) * FFTL_SQRT1_2;
+    yr[2] = b0 + p;
+    yi[2] = -(b2 + m);
+    yr[6] = b0 - p;
+    yi[6] = b2 - m;
+    // odd outputs: c_q = d_q - i d_{q+4}; g_q = c_q W16^q; complex DFT-4 of g gives
+    // Y[1], Y[5], conj(Y[7]), conj(Y[3])
+    float2 g0 = make_float2(d[0], -d[4]);
+    float2 g1 = cmul_w16_1(make_float2(d[1], -d[5]));
+    float2 g2 = cmul_w8_1(make_float2(d[2], -d[6]));
+    float2 g3 = cmul_w16_3(make_float2(d[3], -d[7]));
+    dft4(g0, g1, g2, g3);
+    yr[1] = g0.x; yi[1] = g0.y;
+    yr[5] = g1.x; yi[5] = g1.y;
+    yr[7] = g2.x; yi[7] = -g2.y;
+    yr[3] = g3.x; yi[3] = -g3.y;
+}
+
+template <int N, int F> struct RdifShape {
+    static constexpr int M = N / 16;                 // sub-transform size and pass-A thread count
+    static constexpr int THREADS = M;                // one thread per column
+    static constexpr int SUBG = M / 16;              // lanes per sub-transform
+    static constexpr int SLOT = padded_size(M);      // float2 per slot
+    static constexpr int SLOTS = 8 * F;              // per tile
+    static constexpr int NB = N / 2 + 1;
+    // per-frame magnitude array, padded i -> i + i/16, stride == 16 (mod 32) words
+    static constexpr int MAGP = NB + (NB >> 4) + 1;
+    static constexpr int MAGS = ((MAGP + 31) / 32) * 32 + 16;
+    static size_t smem_bytes(int bars, int nseg)
+    {
+        // segment sums, raw bars and beat heights alias the slot area (dead once pass B/C is done)
+        size_t slots = (size_t)SLOTS * SLOT * sizeof(float2);
+        size_t tail = (size_t)F * (nseg + bars) * sizeof(float) + (size_t)F * 4 * sizeof(int);
+        return (slots > tail ? slots : tail) + (size_t)F * MAGS * sizeof(float);
+    }
+};
+
+template <int N, int F, int HOPQ, bool WINDOWED>
+__global__ void __launch_bounds__(RdifShape<N, F>::THREADS, 2) stft_bars_rdif_kernel(const RdifParams p)
+{
+    using Sh = RdifShape<N, F>;
+    constexpr int M = Sh::M, SUBG = Sh::SUBG, SLOT = Sh::SLOT, MAGS = Sh::MAGS;
+    static_assert(N == 4096, "this instantiation covers N = 4096 (M = 256, two radix-16 sub-passes)");
+    static_assert(F % 2 == 0, "frames are packed in pairs");
+    constexpr int NX = 16 + HOPQ * (F - 1);          // samples per column per tile
+
+    extern __shared__ float2 smem[];
+    float2* slots = smem;                                           // [F/2][16][SLOT]
+    float* segsum = reinterpret_cast<float*>(smem);                 // [F][nseg]   (aliases slots)
+    float* raw = segsum + F * p.nseg;                               // [F][bars]
+    int* beat_h = reinterpret_cast<int*>(raw + F * p.bars_n);       // [F][4]
+    const size_t tail_bytes = (size_t)F * (p.nseg + p.bars_n) * sizeof(float) + (size_t)F * 4 * sizeof(int);
+    const size_t slot_bytes = (size_t)Sh::SLOTS * SLOT * sizeof(float2);
+    float* mags = reinterpret_cast<float*>(reinterpret_cast<char*>(smem) + (slot_bytes > tail_bytes ? slot_bytes : tail_bytes)); // [F][MAGS]
+
+    const int t = threadIdx.x;
+    const int B = p.bars_n;
+
+    // ---- per-thread constants, resident across the whole tile loop
+    float win[16];
+    if (WINDOWED) {
+#pragma unroll
+        for (int q = 0; q < 16; q++) win[q] = __ldg(p.window + t + M * q);
+    }
+    float2 twa[9]; // W_N^(t*k0), k0 = 1..7 ; twa[8] = W_N^(8t)
+#pragma unroll
+    for (int k0 = 1; k0 <= 8; k0++) twa[k0] = __ldg(p.tw + ((t * k0) & (N - 1)));
+    const int j = t & (SUBG - 1);  // lane within the sub-transform
+    const int hw = t / SUBG;       // which slot of a frame pair this half-warp owns
+    float2 twc[16];                // W_M^(j*r), pass C
+#pragma unroll
+    for (int r = 1; r < 16; r++) twc[r] = __ldg(p.twm + j * r);
+
+    for (long long tile = blockIdx.x; tile < p.total_tiles; tile += gridDim.x) {
+        const int ch = (int)(tile / p.tiles_per_channel);
+        const long long f0 = p.frame0 + (tile % p.tiles_per_channel) * F; // first frame of the tile (even)
+        const long long s0 = f0 * (long long)p.hop;                      // its first sample
+        const int16_t* xp = p.pcm + (long long)ch * p.channel_stride + s0 + t;
+
+        // ================= pass A =================
+        float xr[NX];
+        if (s0 + (long long)(NX - 1) * M + M <= p.samples) {
+#pragma unroll
+            for (int r = 0; r < NX; r++) xr[r] = (float)xp[r * M];
+        } else {
+#pragma unroll
+            for (int r = 0; r < NX; r++) xr[r] = (s0 + t + (long long)r * M < p.samples) ? (float)xp[r * M] : 0.0f;
+        }
+#pragma unroll
+        for (int pr = 0; pr < F / 2; pr++) {
+            float2* ps = slots + pr * 16 * SLOT + pad_index(t);
+            float y0[2], y8[2];
+#pragma unroll
+            for (int h = 0; h < 2; h++) {
+                const int f = 2 * pr + h;
+                float x[16], yr[9], yi[9];
+#pragma unroll
+                for (int q = 0; q < 16; q++) x[q] = WINDOWED ? xr[q + HOPQ * f] * win[q] : xr[q + HOPQ * f];
+                real_dft16(x, yr, yi);
+                y0[h] = yr[0];
+                y8[h] = yr[8];
+                // slots 2*k0 + h (k0 = 1..7): frame h of the pair, residue k0
+#pragma unroll
+                for (int k0 = 1; k0 < 8; k0++) ps[(2 * k0 + h) * SLOT] = cmul(make_float2(yr[k0], yi[k0]), twa[k0]);
+            }
+            // slot 0: residue 0 of both frames packed as one complex sequence;
+            // slot 1: residue 8 likewise, twiddled by W_N^(8t)
+            ps[0] = make_float2(y0[0], y0[1]);
+            ps[SLOT] = cmul(make_float2(y8[0], y8[1]), twa[8]);
+        }
+        __syncthreads();
+
+        // ================= pass B/C: one slot per half-warp, warp-level syncs only =================
+        auto wsync = [] { __syncwarp(); };
+#pragma unroll 1
+        for (int pr = 0; pr < F / 2; pr++) {
+            float2* s = slots + (pr * 16 + hw) * SLOT;
+            float2 v[16];
+            stockham_pass<M, 16, 1, SUBG, true>(v, s, p.twm, j, wsync);
+            // second sub-pass with register twiddles; results stay in registers
+#pragma unroll
+            for (int r = 0; r < 16; r++) v[r] = s[pad_index(j + r * (M / 16))];
+#pragma unroll
+            for (int r = 1; r < 16; r++) v[r] = cmul(v[r], twc[r]);
+            Radix<16>::run(v);
+            // v[rr] = Z[m], m = j + 16*kk, kk = out_index(rr)
+            float* magA = mags + (2 * pr) * MAGS;
+            if (hw >= 2) {
+                // regular slot: frame h = hw&1, residue k0 = hw>>1; all 256 outputs are used:
+                // m < 128 directly (bin k0 + 16m), m >= 128 through the conjugate mirror
+                const int k0 = hw >> 1;
+                float* mg = magA + (hw & 1) * MAGS;
+#pragma unroll
+                for (int rr = 0; rr < 16; rr++) {
+                    const int kk = Radix<16>::out_index(rr);
+                    float mag = sqrtf(fmaf(v[rr].x, v[rr].x, v[rr].y * v[rr].y));
+                    int bin = (kk < 8) ? (k0 + 16 * j + 256 * kk) : ((16 - k0) + 16 * (15 - j) + 256 * (15 - kk));
+                    mg[pad_index(bin)] = mag;
+                }
+            } else {
+                // packed slot (hw 0: residue 0, partner m' = 256-m; hw 1: residue 8, partner m' = 255-m)
+                const int src = hw ? (15 - j) : ((16 - j) & 15);
+                const bool self = (hw == 0) && (j == 0);
+#pragma unroll
+                for (int kk = 0; kk < 8; kk++) {
+                    // register holding output kk is rr with out_index(rr) == kk: rr = 4*(kk&3) + (kk>>2)
+                    const int rr = 4 * (kk & 3) + (kk >> 2);
+                    const int kp = 15 - kk, rp = 4 * (kp & 3) + (kp >> 2);
+                    float pr_ = __shfl_sync(0xffffffffu, v[rp].x, src, 16);
+                    float pi_ = __shfl_sync(0xffffffffu, v[rp].y, src, 16);
+                    if (self) {
+                        const int ks = (16 - kk) & 15, rs = 4 * (ks & 3) + (ks >> 2);
+                        pr_ = v[rs].x;
+                        pi_ = v[rs].y;
+                    }
+                    float ar = v[rr].x + pr_, ai = v[rr].y - pi_; // 2 * Xa
+                    float br = v[rr].x - pr_, bi = v[rr].y + pi_; // 2i * Xb
+                    int bin = 16 * (j + 16 * kk) + (hw ? 8 : 0);
+                    magA[pad_index(bin)] = 0.5f * sqrtf(fmaf(ar, ar, ai * ai));
+                    magA[MAGS + pad_index(bin)] = 0.5f * sqrtf(fmaf(br, br, bi * bi));
+                }
+                if (self) {
+                    // m = 128 (bin N/2) is its own partner: Z[128] = Xa[N/2] + i Xb[N/2], both real
+                    const int rr = 4 * (8 & 3) + (8 >> 2);
+                    magA[pad_index(N / 2)] = fabsf(v[rr].x);
+                    magA[MAGS + pad_index(N / 2)] = fabsf(v[rr].y);
+                }
+            }
+        }
+        __syncthreads();
+
+        // ================= bins -> bars (balanced segments), SG, outputs =================
+        for (int it = t; it < F * p.nseg; it += M) {
+            int f = it / p.nseg, sgi = it - f * p.nseg;
+            int l = __ldg(p.seg_lo + sgi), h = __ldg(p.seg_hi + sgi);
+            const float* mg = mags + f * MAGS;
+            float acc = 0.0f;
+            for (int k = l; k < h; k++) acc += mg[pad_index(k)];
+            segsum[it] = acc;
+        }
+        __syncthreads();
+        for (int it = t; it < F * B; it += M) {
+            int f = it / B, b = it - f * B;
+            int a = __ldg(p.bar_seg0 + b), e = __ldg(p.bar_seg0 + b + 1);
+            const float* ss = segsum + f * p.nseg;
+            float acc = 0.0f;
+            for (int k = a; k < e; k++) acc += ss[k];
+            raw[it] = acc * __ldg(p.bar_inv + b);
+        }
+        __syncthreads();
+        const int w = p.sg_half, m = 2 * w + 1;
+        for (int it = t; it < F * B; it += M) {
+            int f = it / B, b = it - f * B;
+            const float* rw = raw + f * B;
+            float y;
+            if (w == 0) y = rw[b];
+            else {
+                int row, base;
+                if (b < w) { row = b; base = 0; }
+                else if (b >= B - w) { row = m - (B - b); base = B - m; }
+                else { row = w; base = b - w; }
+                y = 0.0f;
+                for (int k = 0; k < m; k++) y = fmaf(__ldg(p.sg + row * m + k), rw[base + k], y);
+            }
+            float hgt = y * p.zoom;
+            int ih = trunc_i32(hgt, p.strict);
+            if (p.circle_add != 0.0f) {
+                hgt += p.circle_add;
+                ih = wrap_add(ih, (int)p.circle_add);
+            }
+            const long long fr = f0 + f;
+            if (fr >= p.frame_emit && fr < p.frame_end) {
+                long long o = ((long long)ch * p.nf_emit + (fr - p.frame_emit)) * B + b;
+                p.bars[o] = hgt;
+                if (p.bars_i32) p.bars_i32[o] = ih;
+            }
+#pragma unroll
+            for (int q = 0; q < 4; q++)
+                if (b == p.beat_bars[q]) beat_h[f * 4 + q] = ih;
+        }
+        __syncthreads();
+        if (t < F && p.aux_w) {
+            const long long fr = f0 + t;
+            if (fr < p.frame_end) {
+                const int* h4 = beat_h + 4 * t;
+                int sum = wrap_add(wrap_add(h4[0], h4[1]), wrap_add(h4[2], h4[3]));
+                long long o = (long long)ch * p.nf_aux + (fr - p.aux_base);
+                p.aux_w[o] = sum / 4;                                                       // fft_lines.c:281
+                p.aux_bass[o] = trunc_i32(mags[t * MAGS + pad_index(p.bass_bin)], p.strict); // beatDetector.c:53
+            }
+        }
+        // segsum/raw/beat_h alias the slots the next tile's pass A is about to overwrite
+        __syncthreads();
+    }
+}
+
+} // namespace fftl

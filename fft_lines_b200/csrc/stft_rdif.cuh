@@ -94,15 +94,17 @@ template <int N, int F> struct RdifShape {
     static constexpr int SLOT = padded_size(M);      // float2 per slot
     static constexpr int SLOTS = 8 * F;              // per tile
     static constexpr int NB = N / 2 + 1;
-    // per-frame magnitude array, padded i -> i + i/16, stride == 16 (mod 32) words
-    static constexpr int MAGP = NB + (NB >> 4) + 1;
-    static constexpr int MAGS = ((MAGP + 31) / 32) * 32 + 16;
+    // magnitudes: one float2 array per frame pair (.x = even frame, .y = odd frame), padded
+    // bin -> bin + bin/16: the 16 lanes of a sub-transform (bins 16 apart) then hit 16 distinct
+    // even banks, the other half-warp (odd frame) the odd ones
+    static constexpr int MAGS = padded_size(NB) + 3;
+    __host__ __device__ static size_t tail_bytes(int bars, int nseg) { return (size_t)(nseg + bars) * F * sizeof(float); }
     static size_t smem_bytes(int bars, int nseg)
     {
-        // segment sums, raw bars and beat heights alias the slot area (dead once pass B/C is done)
+        // segment sums and raw bars alias the slot area (dead once pass B/C is done)
         size_t slots = (size_t)SLOTS * SLOT * sizeof(float2);
-        size_t tail = (size_t)F * (nseg + bars) * sizeof(float) + (size_t)F * 4 * sizeof(int);
-        return (slots > tail ? slots : tail) + (size_t)F * MAGS * sizeof(float);
+        size_t tail = tail_bytes(bars, nseg);
+        return (slots > tail ? slots : tail) + (size_t)(F / 2) * MAGS * sizeof(float2) + F * 4 * sizeof(int);
     }
 };
 
@@ -115,14 +117,17 @@ __global__ void __launch_bounds__(RdifShape<N, F>::THREADS, 2) stft_bars_rdif_ke
     static_assert(F % 2 == 0, "frames are packed in pairs");
     constexpr int NX = 16 + HOPQ * (F - 1);          // samples per column per tile
 
+    static_assert(F == 4, "the tail keeps the four frames of a tile in one float4");
     extern __shared__ float2 smem[];
     float2* slots = smem;                                           // [F/2][16][SLOT]
-    float* segsum = reinterpret_cast<float*>(smem);                 // [F][nseg]   (aliases slots)
-    float* raw = segsum + F * p.nseg;                               // [F][bars]
-    int* beat_h = reinterpret_cast<int*>(raw + F * p.bars_n);       // [F][4]
-    const size_t tail_bytes = (size_t)F * (p.nseg + p.bars_n) * sizeof(float) + (size_t)F * 4 * sizeof(int);
+    float4* segsum = reinterpret_cast<float4*>(smem);               // [nseg]  (aliases slots; one lane per frame)
+    float4* raw = segsum + p.nseg;                                  // [bars]
+    const size_t tail_bytes = Sh::tail_bytes(p.bars_n, p.nseg);
     const size_t slot_bytes = (size_t)Sh::SLOTS * SLOT * sizeof(float2);
-    float* mags = reinterpret_cast<float*>(reinterpret_cast<char*>(smem) + (slot_bytes > tail_bytes ? slot_bytes : tail_bytes)); // [F][MAGS]
+    float2* mags = reinterpret_cast<float2*>(reinterpret_cast<char*>(smem) + (slot_bytes > tail_bytes ? slot_bytes : tail_bytes)); // [F/2][MAGS]
+    int* beat_h = reinterpret_cast<int*>(mags + (F / 2) * MAGS);    // [F][4]
+    long long prev_f0 = -1;                                         // tile whose band energy is still to be written
+    int prev_ch = 0;
 
     const int t = threadIdx.x;
     const int B = p.bars_n;
@@ -195,18 +200,21 @@ __global__ void __launch_bounds__(RdifShape<N, F>::THREADS, 2) stft_bars_rdif_ke
             for (int r = 1; r < 16; r++) v[r] = cmul(v[r], twc[r]);
             Radix<16>::run(v);
             // v[rr] = Z[m], m = j + 16*kk, kk = out_index(rr)
-            float* magA = mags + (2 * pr) * MAGS;
+            float2* mg2 = mags + pr * MAGS;
             if (hw >= 2) {
                 // regular slot: frame h = hw&1, residue k0 = hw>>1; all 256 outputs are used:
                 // m < 128 directly (bin k0 + 16m), m >= 128 through the conjugate mirror
                 const int k0 = hw >> 1;
-                float* mg = magA + (hw & 1) * MAGS;
+                float* mg = reinterpret_cast<float*>(mg2) + (hw & 1);
+                // pad_index(k0 + 16j + 256kk) = k0 + 17j + 272kk ; mirror: (16-k0) + 17(15-j) + 272(15-kk)
+                float* lo_base = mg + 2 * (k0 + 17 * j);
+                float* hi_base = mg + 2 * ((16 - k0) + 17 * (15 - j));
 #pragma unroll
                 for (int rr = 0; rr < 16; rr++) {
                     const int kk = Radix<16>::out_index(rr);
                     float mag = sqrtf(fmaf(v[rr].x, v[rr].x, v[rr].y * v[rr].y));
-                    int bin = (kk < 8) ? (k0 + 16 * j + 256 * kk) : ((16 - k0) + 16 * (15 - j) + 256 * (15 - kk));
-                    mg[pad_index(bin)] = mag;
+                    if (kk < 8) lo_base[2 * 272 * kk] = mag;
+                    else hi_base[2 * 272 * (15 - kk)] = mag;
                 }
             } else {
                 // packed slot (hw 0: residue 0, partner m' = 256-m; hw 1: residue 8, partner m' = 255-m)
@@ -227,81 +235,101 @@ __global__ void __launch_bounds__(RdifShape<N, F>::THREADS, 2) stft_bars_rdif_ke
                     float ar = v[rr].x + pr_, ai = v[rr].y - pi_; // 2 * Xa
                     float br = v[rr].x - pr_, bi = v[rr].y + pi_; // 2i * Xb
                     int bin = 16 * (j + 16 * kk) + (hw ? 8 : 0);
-                    magA[pad_index(bin)] = 0.5f * sqrtf(fmaf(ar, ar, ai * ai));
-                    magA[MAGS + pad_index(bin)] = 0.5f * sqrtf(fmaf(br, br, bi * bi));
+                    mg2[pad_index(bin)] = make_float2(0.5f * sqrtf(fmaf(ar, ar, ai * ai)), 0.5f * sqrtf(fmaf(br, br, bi * bi)));
                 }
                 if (self) {
                     // m = 128 (bin N/2) is its own partner: Z[128] = Xa[N/2] + i Xb[N/2], both real
                     const int rr = 4 * (8 & 3) + (8 >> 2);
-                    magA[pad_index(N / 2)] = fabsf(v[rr].x);
-                    magA[MAGS + pad_index(N / 2)] = fabsf(v[rr].y);
+                    mg2[pad_index(N / 2)] = make_float2(fabsf(v[rr].x), fabsf(v[rr].y));
                 }
             }
         }
         __syncthreads();
 
         // ================= bins -> bars (balanced segments), SG, outputs =================
-        for (int it = t; it < F * p.nseg; it += M) {
-            int f = it / p.nseg, sgi = it - f * p.nseg;
-            int l = __ldg(p.seg_lo + sgi), h = __ldg(p.seg_hi + sgi);
-            const float* mg = mags + f * MAGS;
-            float acc = 0.0f;
-            for (int k = l; k < h; k++) acc += mg[pad_index(k)];
-            segsum[it] = acc;
+        // every item carries the tile's four frames in one float4 (x,y = first pair, z,w = second)
+        for (int sgi = t; sgi < p.nseg; sgi += M) {
+            const int l = __ldg(p.seg_lo + sgi), h = __ldg(p.seg_hi + sgi);
+            float4 acc = make_float4(0.f, 0.f, 0.f, 0.f);
+            for (int k = l; k < h; k++) {
+                const int pk = pad_index(k);
+                const float2 a = mags[pk], c = mags[MAGS + pk];
+                acc.x += a.x; acc.y += a.y; acc.z += c.x; acc.w += c.y;
+            }
+            segsum[sgi] = acc;
         }
         __syncthreads();
-        for (int it = t; it < F * B; it += M) {
-            int f = it / B, b = it - f * B;
-            int a = __ldg(p.bar_seg0 + b), e = __ldg(p.bar_seg0 + b + 1);
-            const float* ss = segsum + f * p.nseg;
-            float acc = 0.0f;
-            for (int k = a; k < e; k++) acc += ss[k];
-            raw[it] = acc * __ldg(p.bar_inv + b);
+        for (int b = t; b < B; b += M) {
+            const int a = __ldg(p.bar_seg0 + b), e = __ldg(p.bar_seg0 + b + 1);
+            float4 acc = segsum[a];
+            for (int k = a + 1; k < e; k++) {
+                const float4 u = segsum[k];
+                acc.x += u.x; acc.y += u.y; acc.z += u.z; acc.w += u.w;
+            }
+            const float inv = __ldg(p.bar_inv + b);
+            raw[b] = make_float4(acc.x * inv, acc.y * inv, acc.z * inv, acc.w * inv);
         }
         __syncthreads();
         const int w = p.sg_half, m = 2 * w + 1;
-        for (int it = t; it < F * B; it += M) {
-            int f = it / B, b = it - f * B;
-            const float* rw = raw + f * B;
-            float y;
-            if (w == 0) y = rw[b];
+        for (int b = t; b < B; b += M) {
+            float4 y;
+            if (w == 0) y = raw[b];
             else {
                 int row, base;
                 if (b < w) { row = b; base = 0; }
                 else if (b >= B - w) { row = m - (B - b); base = B - m; }
                 else { row = w; base = b - w; }
-                y = 0.0f;
-                for (int k = 0; k < m; k++) y = fmaf(__ldg(p.sg + row * m + k), rw[base + k], y);
+                y = make_float4(0.f, 0.f, 0.f, 0.f);
+                for (int k = 0; k < m; k++) {
+                    const float c = __ldg(p.sg + row * m + k);
+                    const float4 u = raw[base + k];
+                    y.x = fmaf(c, u.x, y.x); y.y = fmaf(c, u.y, y.y); y.z = fmaf(c, u.z, y.z); y.w = fmaf(c, u.w, y.w);
+                }
             }
-            float hgt = y * p.zoom;
-            int ih = trunc_i32(hgt, p.strict);
-            if (p.circle_add != 0.0f) {
-                hgt += p.circle_add;
-                ih = wrap_add(ih, (int)p.circle_add);
-            }
-            const long long fr = f0 + f;
-            if (fr >= p.frame_emit && fr < p.frame_end) {
-                long long o = ((long long)ch * p.nf_emit + (fr - p.frame_emit)) * B + b;
-                p.bars[o] = hgt;
-                if (p.bars_i32) p.bars_i32[o] = ih;
-            }
+            const float hv[4] = {y.x * p.zoom, y.y * p.zoom, y.z * p.zoom, y.w * p.zoom};
+            int bq = -1;
 #pragma unroll
             for (int q = 0; q < 4; q++)
-                if (b == p.beat_bars[q]) beat_h[f * 4 + q] = ih;
+                if (b == p.beat_bars[q]) bq = q; // duplicates in beat_bars are handled when summing
+#pragma unroll
+            for (int f = 0; f < F; f++) {
+                float hgt = hv[f];
+                int ih = trunc_i32(hgt, p.strict);
+                if (p.circle_add != 0.0f) {
+                    hgt += p.circle_add;
+                    ih = wrap_add(ih, (int)p.circle_add);
+                }
+                const long long fr = f0 + f;
+                if (fr >= p.frame_emit && fr < p.frame_end) {
+                    long long o = ((long long)ch * p.nf_emit + (fr - p.frame_emit)) * B + b;
+                    p.bars[o] = hgt;
+                    if (p.bars_i32) p.bars_i32[o] = ih;
+                }
+                if (bq >= 0) {
+#pragma unroll
+                    for (int q = 0; q < 4; q++)
+                        if (b == p.beat_bars[q]) beat_h[f * 4 + q] = ih;
+                }
+            }
         }
+        // segsum/raw alias the slots the next tile's pass A is about to overwrite; the same barrier
+        // publishes beat_h, which is consumed at the top of the next iteration
         __syncthreads();
+        prev_f0 = f0;
+        prev_ch = ch;
         if (t < F && p.aux_w) {
-            const long long fr = f0 + t;
+            const long long fr = prev_f0 + t;
             if (fr < p.frame_end) {
                 const int* h4 = beat_h + 4 * t;
                 int sum = wrap_add(wrap_add(h4[0], h4[1]), wrap_add(h4[2], h4[3]));
-                long long o = (long long)ch * p.nf_aux + (fr - p.aux_base);
-                p.aux_w[o] = sum / 4;                                                       // fft_lines.c:281
-                p.aux_bass[o] = trunc_i32(mags[t * MAGS + pad_index(p.bass_bin)], p.strict); // beatDetector.c:53
+                const float2 mb = mags[(t >> 1) * MAGS + pad_index(p.bass_bin)];
+                long long o = (long long)prev_ch * p.nf_aux + (fr - p.aux_base);
+                p.aux_w[o] = sum / 4;                                              // fft_lines.c:281
+                p.aux_bass[o] = trunc_i32((t & 1) ? mb.y : mb.x, p.strict);        // beatDetector.c:53
             }
         }
-        // segsum/raw/beat_h alias the slots the next tile's pass A is about to overwrite
-        __syncthreads();
+        // beat_h / mags are rewritten only after the next tile's pass-A barrier (beat_h after its tail
+        // barriers), which these threads reach after the reads above.
     }
 }
 

@@ -360,20 +360,22 @@ extern "C" int fftl_stft_create(const fftl_config* cfg, int device, fftl_stft** 
         H_TRY(cudaMemcpy(h->d_sg, sg.data(), sizeof(float) * m * m, cudaMemcpyHostToDevice));
     }
     {
-        // balanced binning: every bar is cut into segments of at most L bins (at most 8 per bar), so no
-        // lane ever walks a long bin range; partial sums are combined in a fixed order (deterministic)
-        int maxcnt = 1;
-        for (int b = 0; b < B; b++) maxcnt = hi[b] - lo[b] > maxcnt ? hi[b] - lo[b] : maxcnt;
-        int L = (maxcnt + 7) / 8;
-        if (L < 8) L = 8;
+        // balanced binning: every bar is cut into segments of at most 8 bins that never cross a multiple
+        // of 16 (so a segment is contiguous in the padded magnitude array); partial sums are combined in a
+        // fixed order, which keeps the result deterministic
+        const int L = 8;
         std::vector<int> seg_bar, seg_lo, seg_hi, bar_seg0(B + 1);
         std::vector<float> bar_inv(B);
         for (int b = 0; b < B; b++) {
             bar_seg0[b] = (int)seg_lo.size();
-            for (int k = lo[b]; k < hi[b]; k += L) {
+            for (int k = lo[b]; k < hi[b];) {
+                int e = k + L < hi[b] ? k + L : hi[b];
+                int block_end = (k / 16 + 1) * 16;
+                if (e > block_end) e = block_end;
                 seg_bar.push_back(b);
                 seg_lo.push_back(k);
-                seg_hi.push_back(k + L < hi[b] ? k + L : hi[b]);
+                seg_hi.push_back(e);
+                k = e;
             }
             bar_inv[b] = 1.0f / (float)(hi[b] - lo[b]);
         }
@@ -453,19 +455,32 @@ extern "C" int64_t fftl_stft_num_frames(const fftl_stft* h, int64_t samples)
 extern "C" int64_t fftl_stft_launch_count(const fftl_stft* h) { return h ? h->launches : 0; }
 
 // Fast path (stft_rdif.cuh).  Returns cudaErrorNotSupported when the configuration is not covered.
-static const int RDIF_F = 4;
-template <int HOPQ, bool WIN> static cudaError_t launch_rdif(const fftl_stft* h, const RdifParams& p, cudaStream_t st)
+template <int F, int HOPQ, bool WIN, bool RES, int MINB>
+static cudaError_t launch_rdif(const fftl_stft* h, RdifParams p, int channels, cudaStream_t st)
 {
-    using Sh = RdifShape<4096, RDIF_F>;
+    using Sh = RdifShape<4096, F>;
     size_t smem = Sh::smem_bytes(p.bars_n, p.nseg);
-    if (smem > 110 * 1024) return cudaErrorNotSupported; // two CTAs per SM is the design point
-    auto kern = stft_bars_rdif_kernel<4096, RDIF_F, HOPQ, WIN>;
+    if ((smem + 1024) * MINB > 228 * 1024) return cudaErrorNotSupported; // MINB CTAs per SM is the design point
+    p.tiles_per_channel = (p.frame_end - p.frame0 + F - 1) / F;
+    p.total_tiles = p.tiles_per_channel * channels;
+    if (p.total_tiles <= 0) return cudaSuccess;
+    auto kern = stft_bars_rdif_kernel<4096, F, HOPQ, WIN, RES, MINB>;
     cudaError_t e = cudaFuncSetAttribute(kern, cudaFuncAttributeMaxDynamicSharedMemorySize, (int)smem);
     if (e != cudaSuccess) return e;
-    long long grid = 2ll * h->num_sms;
+    long long grid = (long long)MINB * h->num_sms;
     if (grid > p.total_tiles) grid = p.total_tiles;
     kern<<<(unsigned)grid, Sh::THREADS, smem, st>>>(p);
     return cudaGetLastError();
+}
+
+template <int F, bool RES, int MINB>
+static cudaError_t launch_rdif_v(const fftl_stft* h, const RdifParams& p, int channels, int hopq, bool win, cudaStream_t st)
+{
+    switch (hopq) {
+    case 1: return win ? launch_rdif<F, 1, true, RES, MINB>(h, p, channels, st) : launch_rdif<F, 1, false, RES, MINB>(h, p, channels, st);
+    case 2: return win ? launch_rdif<F, 2, true, RES, MINB>(h, p, channels, st) : launch_rdif<F, 2, false, RES, MINB>(h, p, channels, st);
+    default: return win ? launch_rdif<F, 4, true, RES, MINB>(h, p, channels, st) : launch_rdif<F, 4, false, RES, MINB>(h, p, channels, st);
+    }
 }
 
 static cudaError_t try_rdif(const fftl_stft* h, const StftParams& q, int channels, long long samples, cudaStream_t st)
@@ -487,9 +502,6 @@ static cudaError_t try_rdif(const fftl_stft* h, const StftParams& q, int channel
     p.nf_emit = q.nf_emit;
     p.nf_aux = q.nf_aux;
     p.aux_base = q.aux_base;
-    p.tiles_per_channel = (q.frame_end - q.frame0 + RDIF_F - 1) / RDIF_F;
-    p.total_tiles = p.tiles_per_channel * channels;
-    if (p.total_tiles <= 0) return cudaSuccess;
     p.window = q.window;
     p.tw = q.tw;
     p.twm = h->d_twm;
@@ -513,10 +525,16 @@ static cudaError_t try_rdif(const fftl_stft* h, const StftParams& q, int channel
     p.zoom = q.zoom;
     p.circle_add = q.circle_add;
     const bool win = q.window != nullptr;
-    switch (hopq) {
-    case 1: return win ? launch_rdif<1, true>(h, p, st) : launch_rdif<1, false>(h, p, st);
-    case 2: return win ? launch_rdif<2, true>(h, p, st) : launch_rdif<2, false>(h, p, st);
-    default: return win ? launch_rdif<4, true>(h, p, st) : launch_rdif<4, false>(h, p, st);
+    static int variant = -1; // developer A/B switch
+    if (variant < 0) {
+        const char* v = getenv("FFTL_RDIF_VARIANT");
+        variant = v ? atoi(v) : 0;
+    }
+    switch (variant) {
+    case 1: return launch_rdif_v<2, true, 2>(h, p, channels, hopq, win, st);
+    case 2: return launch_rdif_v<2, false, 3>(h, p, channels, hopq, win, st);
+    case 3: return launch_rdif_v<4, false, 2>(h, p, channels, hopq, win, st);
+    default: return launch_rdif_v<4, true, 2>(h, p, channels, hopq, win, st);
     }
 }
 

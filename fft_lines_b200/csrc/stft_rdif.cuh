@@ -108,44 +108,71 @@ template <int N, int F> struct RdifShape {
     }
 };
 
-template <int N, int F, int HOPQ, bool WINDOWED>
-__global__ void __launch_bounds__(RdifShape<N, F>::THREADS, 2) stft_bars_rdif_kernel(const RdifParams p)
+// F floats per tail item, moved as one vector
+template <int F> struct FrameVec;
+template <> struct FrameVec<2> {
+    using type = float2;
+    __device__ __forceinline__ static void load(const float* p, float* v) { float2 u = *reinterpret_cast<const float2*>(p); v[0] = u.x; v[1] = u.y; }
+    __device__ __forceinline__ static void store(float* p, const float* v) { *reinterpret_cast<float2*>(p) = make_float2(v[0], v[1]); }
+};
+template <> struct FrameVec<4> {
+    using type = float4;
+    __device__ __forceinline__ static void load(const float* p, float* v) { float4 u = *reinterpret_cast<const float4*>(p); v[0] = u.x; v[1] = u.y; v[2] = u.z; v[3] = u.w; }
+    __device__ __forceinline__ static void store(float* p, const float* v) { *reinterpret_cast<float4*>(p) = make_float4(v[0], v[1], v[2], v[3]); }
+};
+
+// read-only load that the compiler may not hoist out of the tile loop (keeps the
+// per-thread constant tables out of the register file when RESIDENT is false)
+__device__ __forceinline__ float ldg_pinned(const float* p)
+{
+    float v;
+    asm volatile("ld.global.nc.f32 %0, [%1];" : "=f"(v) : "l"(p));
+    return v;
+}
+__device__ __forceinline__ float2 ldg_pinned(const float2* p)
+{
+    float2 v;
+    asm volatile("ld.global.nc.v2.f32 {%0, %1}, [%2];" : "=f"(v.x), "=f"(v.y) : "l"(p));
+    return v;
+}
+
+template <int N, int F, int HOPQ, bool WINDOWED, bool RESIDENT, int MINB>
+__global__ void __launch_bounds__(RdifShape<N, F>::THREADS, MINB) stft_bars_rdif_kernel(const RdifParams p)
 {
     using Sh = RdifShape<N, F>;
     constexpr int M = Sh::M, SUBG = Sh::SUBG, SLOT = Sh::SLOT, MAGS = Sh::MAGS;
     static_assert(N == 4096, "this instantiation covers N = 4096 (M = 256, two radix-16 sub-passes)");
-    static_assert(F % 2 == 0, "frames are packed in pairs");
+    static_assert(F == 2 || F == 4, "frames are packed in pairs; the tail moves F floats as one vector");
     constexpr int NX = 16 + HOPQ * (F - 1);          // samples per column per tile
 
-    static_assert(F == 4, "the tail keeps the four frames of a tile in one float4");
     extern __shared__ float2 smem[];
     float2* slots = smem;                                           // [F/2][16][SLOT]
-    float4* segsum = reinterpret_cast<float4*>(smem);               // [nseg]  (aliases slots; one lane per frame)
-    float4* raw = segsum + p.nseg;                                  // [bars]
+    float* segsum = reinterpret_cast<float*>(smem);                 // [nseg][F]  (aliases slots)
+    float* raw = segsum + (size_t)p.nseg * F;                       // [bars][F]
     const size_t tail_bytes = Sh::tail_bytes(p.bars_n, p.nseg);
     const size_t slot_bytes = (size_t)Sh::SLOTS * SLOT * sizeof(float2);
     float2* mags = reinterpret_cast<float2*>(reinterpret_cast<char*>(smem) + (slot_bytes > tail_bytes ? slot_bytes : tail_bytes)); // [F/2][MAGS]
     int* beat_h = reinterpret_cast<int*>(mags + (F / 2) * MAGS);    // [F][4]
-    long long prev_f0 = -1;                                         // tile whose band energy is still to be written
-    int prev_ch = 0;
 
     const int t = threadIdx.x;
     const int B = p.bars_n;
-
-    // ---- per-thread constants, resident across the whole tile loop
-    float win[16];
-    if (WINDOWED) {
-#pragma unroll
-        for (int q = 0; q < 16; q++) win[q] = __ldg(p.window + t + M * q);
-    }
-    float2 twa[9]; // W_N^(t*k0), k0 = 1..7 ; twa[8] = W_N^(8t)
-#pragma unroll
-    for (int k0 = 1; k0 <= 8; k0++) twa[k0] = __ldg(p.tw + ((t * k0) & (N - 1)));
     const int j = t & (SUBG - 1);  // lane within the sub-transform
     const int hw = t / SUBG;       // which slot of a frame pair this half-warp owns
-    float2 twc[16];                // W_M^(j*r), pass C
+
+    // ---- per-thread constants: window column, pass-A twiddles W_N^(t*k0), pass-C twiddles W_M^(j*r)
+    float win[16];
+    float2 twa[9];
+    float2 twc[16];
+    if (RESIDENT) {
+        if (WINDOWED) {
 #pragma unroll
-    for (int r = 1; r < 16; r++) twc[r] = __ldg(p.twm + j * r);
+            for (int q = 0; q < 16; q++) win[q] = __ldg(p.window + t + M * q);
+        }
+#pragma unroll
+        for (int k0 = 1; k0 <= 8; k0++) twa[k0] = __ldg(p.tw + t * k0);
+#pragma unroll
+        for (int r = 1; r < 16; r++) twc[r] = __ldg(p.twm + j * r);
+    }
 
     for (long long tile = blockIdx.x; tile < p.total_tiles; tile += gridDim.x) {
         const int ch = (int)(tile / p.tiles_per_channel);
@@ -155,12 +182,20 @@ __global__ void __launch_bounds__(RdifShape<N, F>::THREADS, 2) stft_bars_rdif_ke
 
         // ================= pass A =================
         float xr[NX];
-        if (s0 + (long long)(NX - 1) * M + M <= p.samples) {
+        if (s0 + (long long)NX * M <= p.samples) {
 #pragma unroll
             for (int r = 0; r < NX; r++) xr[r] = (float)xp[r * M];
         } else {
 #pragma unroll
             for (int r = 0; r < NX; r++) xr[r] = (s0 + t + (long long)r * M < p.samples) ? (float)xp[r * M] : 0.0f;
+        }
+        if (!RESIDENT) {
+            if (WINDOWED) {
+#pragma unroll
+                for (int q = 0; q < 16; q++) win[q] = ldg_pinned(p.window + t + M * q);
+            }
+#pragma unroll
+            for (int k0 = 1; k0 <= 8; k0++) twa[k0] = ldg_pinned(p.tw + t * k0);
         }
 #pragma unroll
         for (int pr = 0; pr < F / 2; pr++) {
@@ -193,11 +228,11 @@ __global__ void __launch_bounds__(RdifShape<N, F>::THREADS, 2) stft_bars_rdif_ke
             float2* s = slots + (pr * 16 + hw) * SLOT;
             float2 v[16];
             stockham_pass<M, 16, 1, SUBG, true>(v, s, p.twm, j, wsync);
-            // second sub-pass with register twiddles; results stay in registers
+            // second sub-pass; results stay in registers
 #pragma unroll
             for (int r = 0; r < 16; r++) v[r] = s[pad_index(j + r * (M / 16))];
 #pragma unroll
-            for (int r = 1; r < 16; r++) v[r] = cmul(v[r], twc[r]);
+            for (int r = 1; r < 16; r++) v[r] = cmul(v[r], RESIDENT ? twc[r] : ldg_pinned(p.twm + j * r));
             Radix<16>::run(v);
             // v[rr] = Z[m], m = j + 16*kk, kk = out_index(rr)
             float2* mg2 = mags + pr * MAGS;
@@ -246,90 +281,111 @@ __global__ void __launch_bounds__(RdifShape<N, F>::THREADS, 2) stft_bars_rdif_ke
         }
         __syncthreads();
 
-        // ================= bins -> bars (balanced segments), SG, outputs =================
-        // every item carries the tile's four frames in one float4 (x,y = first pair, z,w = second)
+        // ================= bins -> bars, SG, outputs: every item carries the tile's F frames =================
+        // segments are at most 8 bins long and never cross a multiple of 16, so a segment is 8 consecutive
+        // padded positions at most
         for (int sgi = t; sgi < p.nseg; sgi += M) {
-            const int l = __ldg(p.seg_lo + sgi), h = __ldg(p.seg_hi + sgi);
-            float4 acc = make_float4(0.f, 0.f, 0.f, 0.f);
-            for (int k = l; k < h; k++) {
-                const int pk = pad_index(k);
-                const float2 a = mags[pk], c = mags[MAGS + pk];
-                acc.x += a.x; acc.y += a.y; acc.z += c.x; acc.w += c.y;
+            const int l = __ldg(p.seg_lo + sgi), cnt = __ldg(p.seg_hi + sgi) - l;
+            const float2* m0 = mags + pad_index(l);
+            float acc[F];
+#pragma unroll
+            for (int f = 0; f < F; f++) acc[f] = 0.0f;
+#pragma unroll
+            for (int i = 0; i < 8; i++) {
+                if (i < cnt) {
+#pragma unroll
+                    for (int pr = 0; pr < F / 2; pr++) {
+                        const float2 a = m0[pr * MAGS + i];
+                        acc[2 * pr] += a.x;
+                        acc[2 * pr + 1] += a.y;
+                    }
+                }
             }
-            segsum[sgi] = acc;
+            FrameVec<F>::store(segsum + (size_t)sgi * F, acc);
         }
         __syncthreads();
         for (int b = t; b < B; b += M) {
             const int a = __ldg(p.bar_seg0 + b), e = __ldg(p.bar_seg0 + b + 1);
-            float4 acc = segsum[a];
+            float acc[F];
+            FrameVec<F>::load(segsum + (size_t)a * F, acc);
             for (int k = a + 1; k < e; k++) {
-                const float4 u = segsum[k];
-                acc.x += u.x; acc.y += u.y; acc.z += u.z; acc.w += u.w;
+                float u[F];
+                FrameVec<F>::load(segsum + (size_t)k * F, u);
+#pragma unroll
+                for (int f = 0; f < F; f++) acc[f] += u[f];
             }
             const float inv = __ldg(p.bar_inv + b);
-            raw[b] = make_float4(acc.x * inv, acc.y * inv, acc.z * inv, acc.w * inv);
+#pragma unroll
+            for (int f = 0; f < F; f++) acc[f] *= inv;
+            FrameVec<F>::store(raw + (size_t)b * F, acc);
         }
         __syncthreads();
-        const int w = p.sg_half, m = 2 * w + 1;
-        for (int b = t; b < B; b += M) {
-            float4 y;
-            if (w == 0) y = raw[b];
-            else {
-                int row, base;
-                if (b < w) { row = b; base = 0; }
-                else if (b >= B - w) { row = m - (B - b); base = B - m; }
-                else { row = w; base = b - w; }
-                y = make_float4(0.f, 0.f, 0.f, 0.f);
-                for (int k = 0; k < m; k++) {
-                    const float c = __ldg(p.sg + row * m + k);
-                    const float4 u = raw[base + k];
-                    y.x = fmaf(c, u.x, y.x); y.y = fmaf(c, u.y, y.y); y.z = fmaf(c, u.z, y.z); y.w = fmaf(c, u.w, y.w);
-                }
-            }
-            const float hv[4] = {y.x * p.zoom, y.y * p.zoom, y.z * p.zoom, y.w * p.zoom};
-            int bq = -1;
+        {
+            const int w = p.sg_half, m = 2 * w + 1;
+            // frames of this tile that are emitted: [e_lo, e_hi)
+            const long long dlo = p.frame_emit - f0, dhi = p.frame_end - f0;
+            const int e_lo = dlo > 0 ? (dlo < F ? (int)dlo : F) : 0;
+            const int e_hi = dhi < F ? (dhi > 0 ? (int)dhi : 0) : F;
+            const long long o0 = ((long long)ch * p.nf_emit + (f0 - p.frame_emit)) * B;
+            const bool want_int = (p.bars_i32 != nullptr) || (p.aux_w != nullptr);
+            for (int b = t; b < B; b += M) {
+                float y[F];
+                if (w == 0) FrameVec<F>::load(raw + (size_t)b * F, y);
+                else {
+                    int row, base;
+                    if (b < w) { row = b; base = 0; }
+                    else if (b >= B - w) { row = m - (B - b); base = B - m; }
+                    else { row = w; base = b - w; }
 #pragma unroll
-            for (int q = 0; q < 4; q++)
-                if (b == p.beat_bars[q]) bq = q; // duplicates in beat_bars are handled when summing
+                    for (int f = 0; f < F; f++) y[f] = 0.0f;
+                    const float* cf = p.sg + row * m;
+                    const float* rw = raw + (size_t)base * F;
+                    for (int k = 0; k < m; k++) {
+                        const float c = __ldg(cf + k);
+                        float u[F];
+                        FrameVec<F>::load(rw + (size_t)k * F, u);
 #pragma unroll
-            for (int f = 0; f < F; f++) {
-                float hgt = hv[f];
-                int ih = trunc_i32(hgt, p.strict);
-                if (p.circle_add != 0.0f) {
-                    hgt += p.circle_add;
-                    ih = wrap_add(ih, (int)p.circle_add);
+                        for (int f = 0; f < F; f++) y[f] = fmaf(c, u[f], y[f]);
+                    }
                 }
-                const long long fr = f0 + f;
-                if (fr >= p.frame_emit && fr < p.frame_end) {
-                    long long o = ((long long)ch * p.nf_emit + (fr - p.frame_emit)) * B + b;
-                    p.bars[o] = hgt;
-                    if (p.bars_i32) p.bars_i32[o] = ih;
-                }
-                if (bq >= 0) {
+                float* ob = p.bars + o0 + b;
 #pragma unroll
-                    for (int q = 0; q < 4; q++)
-                        if (b == p.beat_bars[q]) beat_h[f * 4 + q] = ih;
+                for (int f = 0; f < F; f++) {
+                    y[f] *= p.zoom;
+                    if (f >= e_lo && f < e_hi) ob[(long long)f * B] = y[f] + p.circle_add;
+                }
+                if (want_int) {
+                    const bool isbeat = (b == p.beat_bars[0]) | (b == p.beat_bars[1]) | (b == p.beat_bars[2]) | (b == p.beat_bars[3]);
+                    int* oi = p.bars_i32 ? p.bars_i32 + o0 + b : nullptr;
+#pragma unroll
+                    for (int f = 0; f < F; f++) {
+                        const int ih = wrap_add(trunc_i32(y[f], p.strict), (int)p.circle_add);
+                        if (oi && f >= e_lo && f < e_hi) oi[(long long)f * B] = ih;
+                        if (isbeat) {
+#pragma unroll
+                            for (int q = 0; q < 4; q++)
+                                if (b == p.beat_bars[q]) beat_h[f * 4 + q] = ih;
+                        }
+                    }
                 }
             }
         }
         // segsum/raw alias the slots the next tile's pass A is about to overwrite; the same barrier
-        // publishes beat_h, which is consumed at the top of the next iteration
+        // publishes beat_h
         __syncthreads();
-        prev_f0 = f0;
-        prev_ch = ch;
         if (t < F && p.aux_w) {
-            const long long fr = prev_f0 + t;
+            const long long fr = f0 + t;
             if (fr < p.frame_end) {
                 const int* h4 = beat_h + 4 * t;
                 int sum = wrap_add(wrap_add(h4[0], h4[1]), wrap_add(h4[2], h4[3]));
                 const float2 mb = mags[(t >> 1) * MAGS + pad_index(p.bass_bin)];
-                long long o = (long long)prev_ch * p.nf_aux + (fr - p.aux_base);
+                long long o = (long long)ch * p.nf_aux + (fr - p.aux_base);
                 p.aux_w[o] = sum / 4;                                              // fft_lines.c:281
                 p.aux_bass[o] = trunc_i32((t & 1) ? mb.y : mb.x, p.strict);        // beatDetector.c:53
             }
         }
-        // beat_h / mags are rewritten only after the next tile's pass-A barrier (beat_h after its tail
-        // barriers), which these threads reach after the reads above.
+        // beat_h and mags are rewritten only after later barriers of the next tile, which these threads
+        // reach after the reads above.
     }
 }
 

@@ -7,7 +7,7 @@ import ctypes as C
 import os
 
 HERE = os.path.dirname(os.path.abspath(__file__))
-LIB_PATH = os.path.join(HERE, "libfftlines_cuda.so")
+LIB_PATH = os.environ.get("FFTL_LIB") or os.path.join(HERE, "libfftlines_cuda.so")  # FFTL_LIB: developer A/B builds
 
 FFTL_OK, FFTL_ERR_ARG, FFTL_ERR_CUDA, FFTL_ERR_NOMEM, FFTL_ERR_STATE = 0, 1, 2, 3, 4
 WINDOW_RECT, WINDOW_HANN = 0, 1

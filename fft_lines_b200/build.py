@@ -32,18 +32,19 @@ def needs_build():
     return any(os.path.getmtime(f) > t for f in files)
 
 
-def build(force=False, verbose=False, extra=()):
-    if not force and not needs_build():
+def build(force=False, verbose=False, extra=(), out=None):
+    """out: alternative output path (developer A/B builds with extra -D flags)."""
+    if out is None and not force and not needs_build():
         return LIB
     cmd = [nvcc_path(), "-gencode", "arch=compute_100a,code=sm_100a", "-O3", "-lineinfo", "--use_fast_math",
            "-std=c++17", "-shared", "-Xcompiler", "-fPIC,-O2,-fvisibility=default", "-cudart", "static",
-           "-o", LIB] + list(extra) + [os.path.join(CSRC, s) for s in SOURCES]
+           "-o", out or LIB] + list(extra) + [os.path.join(CSRC, s) for s in SOURCES]
     if verbose:
         cmd.insert(1, "-Xptxas")
         cmd.insert(2, "-v")
         print(" ".join(cmd))
     subprocess.check_call(cmd)
-    return LIB
+    return out or LIB
 
 
 if __name__ == "__main__":

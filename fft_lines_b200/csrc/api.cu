@@ -455,16 +455,17 @@ extern "C" int64_t fftl_stft_num_frames(const fftl_stft* h, int64_t samples)
 extern "C" int64_t fftl_stft_launch_count(const fftl_stft* h) { return h ? h->launches : 0; }
 
 // Fast path (stft_rdif.cuh).  Returns cudaErrorNotSupported when the configuration is not covered.
-template <int F, int HOPQ, bool WIN, bool RES, int MINB>
+template <int F, int HOPQ, bool WIN, int SGW>
 static cudaError_t launch_rdif(const fftl_stft* h, RdifParams p, int channels, cudaStream_t st)
 {
+    constexpr int MINB = 2; // two CTAs per SM is the design point (128 registers, ~105 KB shared memory)
     using Sh = RdifShape<4096, F>;
     size_t smem = Sh::smem_bytes(p.bars_n, p.nseg);
-    if ((smem + 1024) * MINB > 228 * 1024) return cudaErrorNotSupported; // MINB CTAs per SM is the design point
+    if ((smem + 1024) * MINB > 228 * 1024) return cudaErrorNotSupported;
     p.tiles_per_channel = (p.frame_end - p.frame0 + F - 1) / F;
     p.total_tiles = p.tiles_per_channel * channels;
     if (p.total_tiles <= 0) return cudaSuccess;
-    auto kern = stft_bars_rdif_kernel<4096, F, HOPQ, WIN, RES, MINB>;
+    auto kern = stft_bars_rdif_kernel<4096, F, HOPQ, WIN, true, MINB, SGW>;
     cudaError_t e = cudaFuncSetAttribute(kern, cudaFuncAttributeMaxDynamicSharedMemorySize, (int)smem);
     if (e != cudaSuccess) return e;
     long long grid = (long long)MINB * h->num_sms;
@@ -473,13 +474,16 @@ static cudaError_t launch_rdif(const fftl_stft* h, RdifParams p, int channels, c
     return cudaGetLastError();
 }
 
-template <int F, bool RES, int MINB>
-static cudaError_t launch_rdif_v(const fftl_stft* h, const RdifParams& p, int channels, int hopq, bool win, cudaStream_t st)
+template <int HOPQ, bool WIN>
+static cudaError_t launch_rdif_sg(const fftl_stft* h, const RdifParams& p, int channels, cudaStream_t st)
 {
-    switch (hopq) {
-    case 1: return win ? launch_rdif<F, 1, true, RES, MINB>(h, p, channels, st) : launch_rdif<F, 1, false, RES, MINB>(h, p, channels, st);
-    case 2: return win ? launch_rdif<F, 2, true, RES, MINB>(h, p, channels, st) : launch_rdif<F, 2, false, RES, MINB>(h, p, channels, st);
-    default: return win ? launch_rdif<F, 4, true, RES, MINB>(h, p, channels, st) : launch_rdif<F, 4, false, RES, MINB>(h, p, channels, st);
+#ifdef FFTL_GENERIC_SG
+    return launch_rdif<4, HOPQ, WIN, -1>(h, p, channels, st);
+#endif
+    switch (p.sg_half) {
+    case 0: return launch_rdif<4, HOPQ, WIN, 0>(h, p, channels, st);
+    case 3: return launch_rdif<4, HOPQ, WIN, 3>(h, p, channels, st);
+    default: return launch_rdif<4, HOPQ, WIN, -1>(h, p, channels, st);
     }
 }
 
@@ -525,16 +529,10 @@ static cudaError_t try_rdif(const fftl_stft* h, const StftParams& q, int channel
     p.zoom = q.zoom;
     p.circle_add = q.circle_add;
     const bool win = q.window != nullptr;
-    static int variant = -1; // developer A/B switch
-    if (variant < 0) {
-        const char* v = getenv("FFTL_RDIF_VARIANT");
-        variant = v ? atoi(v) : 0;
-    }
-    switch (variant) {
-    case 1: return launch_rdif_v<2, true, 2>(h, p, channels, hopq, win, st);
-    case 2: return launch_rdif_v<2, false, 3>(h, p, channels, hopq, win, st);
-    case 3: return launch_rdif_v<4, false, 2>(h, p, channels, hopq, win, st);
-    default: return launch_rdif_v<4, true, 2>(h, p, channels, hopq, win, st);
+    switch (hopq) {
+    case 1: return win ? launch_rdif_sg<1, true>(h, p, channels, st) : launch_rdif_sg<1, false>(h, p, channels, st);
+    case 2: return win ? launch_rdif_sg<2, true>(h, p, channels, st) : launch_rdif_sg<2, false>(h, p, channels, st);
+    default: return win ? launch_rdif_sg<4, true>(h, p, channels, st) : launch_rdif_sg<4, false>(h, p, channels, st);
     }
 }
 
@@ -601,7 +599,8 @@ static int run_range(fftl_stft* h, const int16_t* pcm, int channels, int64_t cst
         float dt = (float)c.hop / c.sample_rate;  // timeDelta of a batch run (fft_lines.c:265 uses wall clock)
         bp.n_times_dt = (float)c.n * dt;          // beatDetector.c:105, left-to-right in float
         bp.strict = c.strict_int;
-        dim3 grid((unsigned)((fe - fb + BEAT_FRAMES_PER_CTA - 1) / BEAT_FRAMES_PER_CTA), (unsigned)channels);
+        const int64_t fb_even = fb & ~(int64_t)1;
+        dim3 grid((unsigned)((fe - fb_even + BEAT_FB - 1) / BEAT_FB), (unsigned)channels);
         beat_post_kernel<<<grid, 256, 0, st>>>(bp);
         CUDA_TRY(cudaGetLastError());
         h->launches++;
@@ -631,7 +630,7 @@ extern "C" int fftl_stft_run_device(fftl_stft* h, const int16_t* pcm, int32_t ch
     cudaStream_t st = (cudaStream_t)cuda_stream; // NULL = CUDA's default stream, as everywhere in CUDA
     int64_t warm = fb;
     if (beat) {
-        warm = fb - (FFTL_TEMPO_RING - 1);
+        warm = fb - FFTL_TEMPO_RING; // 255 frames of history for fb, one more for its pair partner fb^1
         if (warm < 0) warm = 0;
     }
     warm &= ~(int64_t)1; // frame f always shares its transform with frame f^1: results do not depend on the shard start
@@ -694,7 +693,7 @@ extern "C" int fftl_stft_run(fftl_stft* h, const int16_t* pcm, int32_t channels,
     const bool interleaved = (sstride != 1);
     int64_t warm = fb;
     if (beat) {
-        warm = fb - (FFTL_TEMPO_RING - 1);
+        warm = fb - FFTL_TEMPO_RING;
         if (warm < 0) warm = 0;
     }
     warm &= ~(int64_t)1; // same pairing as the device path (chunks are even-sized)

@@ -210,7 +210,7 @@ struct BeatParams {
     int strict;
 };
 
-// Peak scan of beatDetector.c:78-103 done by one warp on hb[0..160].
+// Peak scan of beatDetector.c:78-103 done by one warp on hb[0..160] (drop-in path).
 __device__ __forceinline__ int warp_peak_pick(const int* hb, int lane)
 {
     int rank_base = 0;
@@ -247,59 +247,174 @@ __device__ __forceinline__ int warp_peak_pick(const int* hb, int lane)
     return first_peak >= 0 ? first_peak : 0;
 }
 
-constexpr int BEAT_FRAMES_PER_CTA = 16;
 constexpr int HB_STRIDE = FFTL_BEAT_SAMPLES + 2;
+
+// Cross-frame stage for a block of 32 consecutive frames of one channel.
+//   - bass / band-energy history of the block is staged in shared memory once;
+//   - frames f and f^1 share one complex 256-point transform of their two tempo
+//     rings (the reference feeds a real ring into a complex FFT, beatDetector.c:61-67),
+//     done by 16 lanes with warp-level syncs and untangled with shuffles;
+//   - the peak scan of a frame is split over 8 lanes (20 bins each);
+//   - AddBeatSample's 160-frame running sum is a difference of integer prefix sums.
+constexpr int BEAT_FB = 32;
+constexpr int BEAT_HBS = padded_size(FFTL_TEMPO_RING); // a frame's heightBuffer reuses half of its pair's transform buffer
 
 __global__ void __launch_bounds__(256) beat_post_kernel(const BeatParams p)
 {
-    __shared__ float2 sf[BEAT_FRAMES_PER_CTA][padded_size(FFTL_TEMPO_RING)];
-    __shared__ int hbs[BEAT_FRAMES_PER_CTA][HB_STRIDE];
-    const int grp = threadIdx.x >> 4, g = threadIdx.x & 15;
+    __shared__ int s_bass[BEAT_FB + FFTL_TEMPO_RING];          // frame fbase-256+i
+    __shared__ unsigned s_pre[BEAT_FB + FFTL_BEAT_SAMPLES + 1]; // prefix sums of w from frame fbase-159
+    __shared__ float2 s_tw[FFTL_TEMPO_RING];
+    __shared__ float2 sf[BEAT_FB / 2][padded_size(FFTL_TEMPO_RING)];
+    const int tid = threadIdx.x;
     const int ch = blockIdx.y;
-    const long long f = p.frame_emit + (long long)blockIdx.x * BEAT_FRAMES_PER_CTA + grp;
-    const bool valid = f < p.frame_end;
+    const long long fbase = (p.frame_emit & ~1ll) + (long long)blockIdx.x * BEAT_FB; // even: pairs are (f, f^1)
     const int* bass = p.aux_bass + (long long)ch * p.nf_aux;
     const int* wv = p.aux_w + (long long)ch * p.nf_aux;
-    auto sync = [] { __syncthreads(); };
+    const long long avail_lo = p.aux_base, avail_hi = p.frame_end; // frames whose (w, bass) exist
 
-    // ring in ring order: slot i holds the newest frame j <= f with j % 256 == i
-    // (beatDetector.c:53-65; the ring starts zeroed, settingsFile.c:295-301)
-    float2 v[16];
-#pragma unroll
-    for (int r = 0; r < 16; r++) {
-        int i = g + 16 * r;
-        long long j = f - (long long)((unsigned)(f - i) & (FFTL_TEMPO_RING - 1));
-        int val = (valid && j >= 0) ? __ldg(bass + (j - p.aux_base)) : 0;
-        v[r] = make_float2((float)val, 0.0f);
+    // ---- stage history
+    for (int i = tid; i < BEAT_FB + FFTL_TEMPO_RING; i += 256) {
+        long long fr = fbase - FFTL_TEMPO_RING + i;
+        s_bass[i] = (fr >= avail_lo && fr < avail_hi) ? __ldg(bass + (fr - p.aux_base)) : 0; // ring starts zeroed
     }
-    float2* s = sf[grp];
-    stockham_pass<256, 16, 1, 16, false>(v, s, p.tw256, g, sync);
-    stockham_pass<256, 16, 16, 16, true>(v, s, p.tw256, g, sync);
-    // heightBuffer (beatDetector.c:69-75) plus the [160] the reference reads out of bounds
-    for (int i = g; i <= FFTL_BEAT_SAMPLES; i += 16) {
-        float2 z = s[pad_index(i)];
-        hbs[grp][i] = trunc_i32(sqrtf(fmaf(z.x, z.x, z.y * z.y)), p.strict);
+    s_tw[tid] = __ldg(p.tw256 + tid);
+    // inclusive-exclusive prefix of w over frames fbase-159 .. fbase+31 (191 values) by warp 0:
+    // s_pre[i] = sum of the first i values, so sum(frames f-159..f) = s_pre[f-fbase+160] - s_pre[f-fbase]
+    if (tid < 32) {
+        constexpr int PER = 6; // 32 lanes * 6 = 192 >= 191
+        unsigned loc[PER], run = 0;
+#pragma unroll
+        for (int q = 0; q < PER; q++) {
+            int i = tid * PER + q;
+            long long fr = fbase - (FFTL_BEAT_SAMPLES - 1) + i;
+            unsigned v = (i < BEAT_FB + FFTL_BEAT_SAMPLES - 1 && fr >= avail_lo && fr < avail_hi) ? (unsigned)__ldg(wv + (fr - p.aux_base)) : 0u;
+            run += v;
+            loc[q] = run;
+        }
+        unsigned incl = run;
+#pragma unroll
+        for (int o = 1; o < 32; o <<= 1) {
+            unsigned n = __shfl_up_sync(0xffffffffu, incl, o);
+            if (tid >= o) incl += n;
+        }
+        unsigned excl = incl - run;
+        if (tid == 0) s_pre[0] = 0;
+#pragma unroll
+        for (int q = 0; q < PER; q++) {
+            int i = tid * PER + q;
+            if (i < BEAT_FB + FFTL_BEAT_SAMPLES) s_pre[i + 1] = excl + loc[q];
+        }
     }
     __syncthreads();
 
-    const int warp = threadIdx.x >> 5, lane = threadIdx.x & 31;
+    // ---- one frame pair per 16 lanes
+    {
+        const int grp = tid >> 4, l = tid & 15;
+        const long long fa = fbase + 2 * grp; // ring slot i holds the newest frame j <= f with j % 256 == i
+        const int fa_m = (int)(fa & (FFTL_TEMPO_RING - 1));
+        const int fb_slot = (fa_m + 1) & (FFTL_TEMPO_RING - 1);
+        const int newest_b = s_bass[FFTL_TEMPO_RING + 2 * grp + 1];
+        auto sync16 = [] { __syncwarp(); };
+        float2 v[16];
 #pragma unroll
-    for (int q = 0; q < 2; q++) {
-        const int fr = 2 * warp + q;
-        const long long ff = p.frame_emit + (long long)blockIdx.x * BEAT_FRAMES_PER_CTA + fr;
-        if (ff >= p.frame_end) continue; // uniform per warp
-        int peak = warp_peak_pick(hbs[fr], lane);
-        // AddBeatSample: sum of the last 160 band energies (ring starts zeroed)
-        int part = 0;
+        for (int r = 0; r < 16; r++) {
+            int i = l + 16 * r;
+            int back = (fa_m - i) & (FFTL_TEMPO_RING - 1);            // frames back from fa
+            int a = s_bass[FFTL_TEMPO_RING + 2 * grp - back];           // beatDetector.c:61-65
+            int b = (i == fb_slot) ? newest_b : a;                      // frame fa+1 overwrote one slot
+            v[r] = make_float2((float)a, (float)b);
+        }
+        float2* s = sf[grp];
+        stockham_pass<256, 16, 1, 16, false>(v, s, s_tw, l, sync16);
 #pragma unroll
-        for (int c = 0; c < FFTL_BEAT_SAMPLES / 32; c++) {
-            long long j = ff - (lane + 32 * c);
-            if (j >= 0) part = wrap_add(part, __ldg(wv + (j - p.aux_base)));
+        for (int r = 0; r < 16; r++) v[r] = s[pad_index(l + 16 * r)];
+#pragma unroll
+        for (int r = 1; r < 16; r++) v[r] = cmul(v[r], s_tw[l * r]);
+        Radix<16>::run(v);
+        __syncwarp(); // every lane has read its inputs: the buffer can now hold the two heightBuffers
+        // untangle bins k = l + 16*kk <= 160 of both frames; partner 256-k sits in lane (16-l)&15
+        const int src = (16 - l) & 15;
+        int* ha = reinterpret_cast<int*>(s);
+        int* hb = ha + BEAT_HBS;
+#pragma unroll
+        for (int kk = 0; kk <= 10; kk++) {
+            const int rr = 4 * (kk & 3) + (kk >> 2);
+            const int kp = 15 - kk, rp = 4 * (kp & 3) + (kp >> 2);
+            float pr_ = __shfl_sync(0xffffffffu, v[rp].x, src, 16);
+            float pi_ = __shfl_sync(0xffffffffu, v[rp].y, src, 16);
+            if (l == 0) {
+                const int ks = (16 - kk) & 15, rs = 4 * (ks & 3) + (ks >> 2);
+                pr_ = v[rs].x;
+                pi_ = v[rs].y;
+            }
+            float ar = v[rr].x + pr_, ai = v[rr].y - pi_;
+            float br = v[rr].x - pr_, bi = v[rr].y + pi_;
+            const int k = l + 16 * kk;
+            if (k <= FFTL_BEAT_SAMPLES) {                               // beatDetector.c:69-75 (+ the [160] it reads OOB)
+                ha[k] = trunc_i32(0.5f * sqrtf(fmaf(ar, ar, ai * ai)), p.strict);
+                hb[k] = trunc_i32(0.5f * sqrtf(fmaf(br, br, bi * bi)), p.strict);
+            }
+        }
+    }
+    __syncthreads();
+
+    // ---- peak scan (beatDetector.c:78-103): 8 lanes per frame, 20 bins each
+    {
+        const int fr_i = tid >> 3, sub = tid & 7;
+        const long long f = fbase + fr_i;
+        const int* h = reinterpret_cast<const int*>(sf[fr_i >> 1]) + (fr_i & 1) * BEAT_HBS;
+        const int i0 = 20 * sub;
+        unsigned bits = 0;
+        int prev = (i0 == 0) ? 0 : h[i0 - 1];
+        int cur = h[i0];
+#pragma unroll
+        for (int q = 0; q < 20; q++) {
+            int nxt = h[i0 + q + 1];
+            int dold = (i0 + q == 0) ? 0 : wrap_sub(cur, prev);
+            int dnew = wrap_sub(nxt, cur);
+            if (dold >= 0 && dnew <= 0) bits |= 1u << q;
+            prev = cur;
+            cur = nxt;
+        }
+        // peaks before this lane's range (lanes of a frame are consecutive lanes of the warp)
+        int cnt = __popc(bits), incl = cnt;
+#pragma unroll
+        for (int o = 1; o < 8; o <<= 1) {
+            int n = __shfl_up_sync(0xffffffffu, incl, o, 8);
+            if (sub >= o) incl += n;
+        }
+        int rank = incl - cnt;
+        int best_val = 0, best_idx = -1;
+        int first = bits ? (i0 + __ffs(bits) - 1) : 1 << 30;
+        unsigned bb = bits;
+        while (bb) {
+            int q = __ffs(bb) - 1;
+            bb &= bb - 1;
+            int i = i0 + q;
+            int hv = h[i];
+            if (rank < 30 && i > 30 && hv > best_val) { // only the first 30 peaks are looked at
+                best_val = hv;
+                best_idx = i;
+            }
+            rank++;
         }
 #pragma unroll
-        for (int o = 16; o > 0; o >>= 1) part = wrap_add(part, __shfl_xor_sync(0xffffffffu, part, o));
-        if (lane == 0) {
-            int wcur = __ldg(wv + (ff - p.aux_base));
+        for (int o = 4; o > 0; o >>= 1) {
+            int ov = __shfl_xor_sync(0xffffffffu, best_val, o, 8);
+            int oi = __shfl_xor_sync(0xffffffffu, best_idx, o, 8);
+            int of = __shfl_xor_sync(0xffffffffu, first, o, 8);
+            bool take = (oi >= 0) && (best_idx < 0 || ov > best_val || (ov == best_val && oi < best_idx));
+            if (take) {
+                best_val = ov;
+                best_idx = oi;
+            }
+            first = of < first ? of : first;
+        }
+        if (sub == 0 && f >= p.frame_emit && f < p.frame_end) {
+            int peak = best_idx >= 0 ? best_idx : (first < (1 << 30) ? first : 0);
+            // AddBeatSample: sum of the last 160 band energies (beatDetector.c:32-41)
+            int part = (int)(s_pre[fr_i + FFTL_BEAT_SAMPLES] - s_pre[fr_i]);
+            int wcur = (int)(s_pre[fr_i + FFTL_BEAT_SAMPLES] - s_pre[fr_i + FFTL_BEAT_SAMPLES - 1]);
             int thr = part / FFTL_BEAT_SAMPLES;                 // beatDetector.c:41
             float qv = __fdiv_rn((float)wcur, (float)thr);      // IEEE: x/0 = inf, 0/0 = NaN
             int bv = trunc_i32(__fmul_rn(qv, 128.0f), 1);       // beatDetector.c:43 (always x86 semantics)
@@ -308,11 +423,11 @@ __global__ void __launch_bounds__(256) beat_post_kernel(const BeatParams p)
             rec.thr = thr;
             rec.beat_value = bv;
             rec.flag = (thr > 0 && wcur > thr) ? 1 : 0;
-            rec.bass = __ldg(bass + (ff - p.aux_base));
+            rec.bass = s_bass[FFTL_TEMPO_RING + fr_i];
             rec.peak_index = peak;
             rec.movement_per_sec = __fmul_rn(p.n_times_dt, (float)peak); // beatDetector.c:105
             rec.reserved = 0;
-            p.out[(long long)ch * p.nf_emit + (ff - p.frame_emit)] = rec;
+            p.out[(long long)ch * p.nf_emit + (f - p.frame_emit)] = rec;
         }
     }
 }

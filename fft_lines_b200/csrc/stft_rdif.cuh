@@ -136,7 +136,35 @@ __device__ __forceinline__ float2 ldg_pinned(const float2* p)
     return v;
 }
 
-template <int N, int F, int HOPQ, bool WINDOWED, bool RESIDENT, int MINB>
+// Savitzky-Golay over the raw bar vector for F frames at once; TAPS < 0: run-time width.
+template <int F, int TAPS>
+__device__ __forceinline__ void sg_apply(const float* __restrict__ cf, const float* rw, int m, float* y)
+{
+#pragma unroll
+    for (int f = 0; f < F; f++) y[f] = 0.0f;
+    if (TAPS > 0) {
+#pragma unroll
+        for (int k = 0; k < TAPS; k++) {
+            const float c = __ldg(cf + k);
+            float u[F];
+            FrameVec<F>::load(rw + k * F, u);
+#pragma unroll
+            for (int f = 0; f < F; f++) y[f] = fmaf(c, u[f], y[f]);
+        }
+    } else {
+#pragma unroll 1
+        for (int k = 0; k < m; k++) {
+            const float c = __ldg(cf + k);
+            float u[F];
+            FrameVec<F>::load(rw + k * F, u);
+#pragma unroll
+            for (int f = 0; f < F; f++) y[f] = fmaf(c, u[f], y[f]);
+        }
+    }
+}
+
+// SGW: compile-time Savitzky-Golay half width (0 = off, 3 = the default) or -1 for any run-time width.
+template <int N, int F, int HOPQ, bool WINDOWED, bool RESIDENT, int MINB, int SGW>
 __global__ void __launch_bounds__(RdifShape<N, F>::THREADS, MINB) stft_bars_rdif_kernel(const RdifParams p)
 {
     using Sh = RdifShape<N, F>;
@@ -148,7 +176,7 @@ __global__ void __launch_bounds__(RdifShape<N, F>::THREADS, MINB) stft_bars_rdif
     extern __shared__ float2 smem[];
     float2* slots = smem;                                           // [F/2][16][SLOT]
     float* segsum = reinterpret_cast<float*>(smem);                 // [nseg][F]  (aliases slots)
-    float* raw = segsum + (size_t)p.nseg * F;                       // [bars][F]
+    float* raw = segsum + p.nseg * F;                       // [bars][F]
     const size_t tail_bytes = Sh::tail_bytes(p.bars_n, p.nseg);
     const size_t slot_bytes = (size_t)Sh::SLOTS * SLOT * sizeof(float2);
     float2* mags = reinterpret_cast<float2*>(reinterpret_cast<char*>(smem) + (slot_bytes > tail_bytes ? slot_bytes : tail_bytes)); // [F/2][MAGS]
@@ -174,21 +202,37 @@ __global__ void __launch_bounds__(RdifShape<N, F>::THREADS, MINB) stft_bars_rdif
         for (int r = 1; r < 16; r++) twc[r] = __ldg(p.twm + j * r);
     }
 
+    // Samples of the NEXT tile are fetched (raw int16) while the current tile's tail runs, so pass A
+    // never waits on global memory.  xraw is live across the tail only.
+    int xraw[NX];
+    auto fetch = [&](long long tile) {
+        const int ch = (int)(tile / p.tiles_per_channel);
+        const long long f0 = p.frame0 + (tile % p.tiles_per_channel) * F;
+        const long long s0 = f0 * (long long)p.hop;
+        const int16_t* xp = p.pcm + (long long)ch * p.channel_stride + s0 + t;
+        if (s0 + (long long)NX * M <= p.samples) {
+#pragma unroll
+            for (int r = 0; r < NX; r++) xraw[r] = xp[r * M];
+        } else {
+#pragma unroll
+            for (int r = 0; r < NX; r++) xraw[r] = (s0 + t + (long long)r * M < p.samples) ? (int)xp[r * M] : 0;
+        }
+    };
+#ifdef FFTL_REG_PREFETCH
+    if ((long long)blockIdx.x < p.total_tiles) fetch(blockIdx.x);
+#endif
+
     for (long long tile = blockIdx.x; tile < p.total_tiles; tile += gridDim.x) {
         const int ch = (int)(tile / p.tiles_per_channel);
         const long long f0 = p.frame0 + (tile % p.tiles_per_channel) * F; // first frame of the tile (even)
-        const long long s0 = f0 * (long long)p.hop;                      // its first sample
-        const int16_t* xp = p.pcm + (long long)ch * p.channel_stride + s0 + t;
 
         // ================= pass A =================
+#ifndef FFTL_REG_PREFETCH
+        fetch(tile);
+#endif
         float xr[NX];
-        if (s0 + (long long)NX * M <= p.samples) {
 #pragma unroll
-            for (int r = 0; r < NX; r++) xr[r] = (float)xp[r * M];
-        } else {
-#pragma unroll
-            for (int r = 0; r < NX; r++) xr[r] = (s0 + t + (long long)r * M < p.samples) ? (float)xp[r * M] : 0.0f;
-        }
+        for (int r = 0; r < NX; r++) xr[r] = (float)xraw[r];
         if (!RESIDENT) {
             if (WINDOWED) {
 #pragma unroll
@@ -280,6 +324,21 @@ __global__ void __launch_bounds__(RdifShape<N, F>::THREADS, MINB) stft_bars_rdif
             }
         }
         __syncthreads();
+#ifdef FFTL_REG_PREFETCH
+        if (tile + gridDim.x < p.total_tiles) fetch(tile + gridDim.x);
+#endif
+#ifdef FFTL_L2_PREFETCH
+        if (tile + gridDim.x < p.total_tiles) {
+            const long long nt = tile + gridDim.x;
+            const int nch = (int)(nt / p.tiles_per_channel);
+            const long long ns0 = (p.frame0 + (nt % p.tiles_per_channel) * F) * (long long)p.hop;
+            const int16_t* np_ = p.pcm + (long long)nch * p.channel_stride + ns0 + t;
+            if (ns0 + (long long)NX * M <= p.samples) {
+#pragma unroll
+                for (int r = 0; r < NX; r++) asm volatile("prefetch.global.L2 [%0];" ::"l"(np_ + r * M));
+            }
+        }
+#endif
 
         // ================= bins -> bars, SG, outputs: every item carries the tile's F frames =================
         // segments are at most 8 bins long and never cross a multiple of 16, so a segment is 8 consecutive
@@ -301,70 +360,64 @@ __global__ void __launch_bounds__(RdifShape<N, F>::THREADS, MINB) stft_bars_rdif
                     }
                 }
             }
-            FrameVec<F>::store(segsum + (size_t)sgi * F, acc);
+            FrameVec<F>::store(segsum + sgi * F, acc);
         }
         __syncthreads();
         for (int b = t; b < B; b += M) {
             const int a = __ldg(p.bar_seg0 + b), e = __ldg(p.bar_seg0 + b + 1);
             float acc[F];
-            FrameVec<F>::load(segsum + (size_t)a * F, acc);
+            FrameVec<F>::load(segsum + a * F, acc);
             for (int k = a + 1; k < e; k++) {
                 float u[F];
-                FrameVec<F>::load(segsum + (size_t)k * F, u);
+                FrameVec<F>::load(segsum + k * F, u);
 #pragma unroll
                 for (int f = 0; f < F; f++) acc[f] += u[f];
             }
             const float inv = __ldg(p.bar_inv + b);
 #pragma unroll
             for (int f = 0; f < F; f++) acc[f] *= inv;
-            FrameVec<F>::store(raw + (size_t)b * F, acc);
+            FrameVec<F>::store(raw + b * F, acc);
         }
         __syncthreads();
         {
-            const int w = p.sg_half, m = 2 * w + 1;
+            const int w = SGW >= 0 ? SGW : p.sg_half, m = 2 * w + 1;
             // frames of this tile that are emitted: [e_lo, e_hi)
             const long long dlo = p.frame_emit - f0, dhi = p.frame_end - f0;
             const int e_lo = dlo > 0 ? (dlo < F ? (int)dlo : F) : 0;
             const int e_hi = dhi < F ? (dhi > 0 ? (int)dhi : 0) : F;
             const long long o0 = ((long long)ch * p.nf_emit + (f0 - p.frame_emit)) * B;
             const bool want_int = (p.bars_i32 != nullptr) || (p.aux_w != nullptr);
+#pragma unroll 1
             for (int b = t; b < B; b += M) {
                 float y[F];
-                if (w == 0) FrameVec<F>::load(raw + (size_t)b * F, y);
+                if (w == 0) FrameVec<F>::load(raw + b * F, y);
                 else {
                     int row, base;
                     if (b < w) { row = b; base = 0; }
                     else if (b >= B - w) { row = m - (B - b); base = B - m; }
                     else { row = w; base = b - w; }
-#pragma unroll
-                    for (int f = 0; f < F; f++) y[f] = 0.0f;
-                    const float* cf = p.sg + row * m;
-                    const float* rw = raw + (size_t)base * F;
-                    for (int k = 0; k < m; k++) {
-                        const float c = __ldg(cf + k);
-                        float u[F];
-                        FrameVec<F>::load(rw + (size_t)k * F, u);
-#pragma unroll
-                        for (int f = 0; f < F; f++) y[f] = fmaf(c, u[f], y[f]);
-                    }
+                    sg_apply<F, (SGW > 0 ? 2 * SGW + 1 : -1)>(p.sg + row * m, raw + base * F, m, y);
                 }
-                float* ob = p.bars + o0 + b;
+                float* ob = p.bars + (o0 + b);
 #pragma unroll
                 for (int f = 0; f < F; f++) {
                     y[f] *= p.zoom;
-                    if (f >= e_lo && f < e_hi) ob[(long long)f * B] = y[f] + p.circle_add;
+                    if (f >= e_lo && f < e_hi) ob[f * B] = y[f] + p.circle_add;
                 }
                 if (want_int) {
                     const bool isbeat = (b == p.beat_bars[0]) | (b == p.beat_bars[1]) | (b == p.beat_bars[2]) | (b == p.beat_bars[3]);
-                    int* oi = p.bars_i32 ? p.bars_i32 + o0 + b : nullptr;
+                    if (p.bars_i32 || isbeat) {
+                        int* oi = p.bars_i32 ? p.bars_i32 + (o0 + b) : nullptr;
+                        const int cadd = (int)p.circle_add;
 #pragma unroll
-                    for (int f = 0; f < F; f++) {
-                        const int ih = wrap_add(trunc_i32(y[f], p.strict), (int)p.circle_add);
-                        if (oi && f >= e_lo && f < e_hi) oi[(long long)f * B] = ih;
-                        if (isbeat) {
+                        for (int f = 0; f < F; f++) {
+                            const int ih = wrap_add(trunc_i32(y[f], p.strict), cadd);
+                            if (oi && f >= e_lo && f < e_hi) oi[f * B] = ih;
+                            if (isbeat) {
 #pragma unroll
-                            for (int q = 0; q < 4; q++)
-                                if (b == p.beat_bars[q]) beat_h[f * 4 + q] = ih;
+                                for (int q = 0; q < 4; q++)
+                                    if (b == p.beat_bars[q]) beat_h[f * 4 + q] = ih;
+                            }
                         }
                     }
                 }

@@ -286,7 +286,7 @@ def main():
             with open(tp) as f:
                 traffic = json.load(f).get("stft_bars_dram_bytes_per_launch")
         roof = {
-            "bound": "fp32", "kernel": "stft_bars_kernel<4096>",
+            "bound": "fp32", "kernel": "stft_bars_rdif_kernel<4096> (fast path; generic fallback: stft_bars_kernel<N>)",
             "achieved": achieved_tf, "peak": fp32_peak, "unit": "TFLOP/s", "frac": achieved_tf / fp32_peak,
             "peak_source": "FP32 FMA probe run in this process (not in MEASURED_PEAKS.json); nominal %.2f" % NOMINAL_FP32_TFLOPS,
             "frac_of_nominal": achieved_tf / NOMINAL_FP32_TFLOPS,

@@ -304,7 +304,7 @@ def main():
                        "seconds": args.seconds, "frames_per_step_per_gpu": frames_per_step,
                        "sharding": "one batch per GPU, no data-path collective",
                        "l2": "input %d MB per step > 126 MB L2, no flush needed" % (CHANNELS * S * 2 // 1000000)},
-            "clocks": clocks, "e2e": e2e, "gpu_launches": int(launches), "roofline": roof, "cpu_baseline": cpu,
+            "clocks": clocks, "e2e": e2e, "gpu_launches": int(launches) * world, "roofline": roof, "cpu_baseline": cpu,
         }
         print(json.dumps(line), flush=True)
     sp.close()

@@ -175,10 +175,14 @@ __global__ void __launch_bounds__(RdifShape<N, F>::THREADS, MINB) stft_bars_rdif
 
     extern __shared__ float2 smem[];
     float2* slots = smem;                                           // [F/2][16][SLOT]
-    float* segsum = reinterpret_cast<float*>(smem);                 // [nseg][F]  (aliases slots)
-    float* raw = segsum + p.nseg * F;                       // [bars][F]
     const size_t tail_bytes = Sh::tail_bytes(p.bars_n, p.nseg);
     const size_t slot_bytes = (size_t)Sh::SLOTS * SLOT * sizeof(float2);
+    // The tail's segment sums / raw bars alias the END of the slot area, i.e. slots of the LAST frame pair:
+    // the next tile's pass A may then write the first pair's slots while slow warps still finish this tile's
+    // tail; the barrier that protects the aliased part sits in the middle of pass A (LATE_ALIAS).
+    const bool late_alias = (F == 4) && tail_bytes <= (size_t)16 * SLOT * sizeof(float2);
+    float* segsum = reinterpret_cast<float*>(reinterpret_cast<char*>(smem) + (late_alias ? slot_bytes - tail_bytes : 0)); // [nseg][F]
+    float* raw = segsum + p.nseg * F;                               // [bars][F]
     float2* mags = reinterpret_cast<float2*>(reinterpret_cast<char*>(smem) + (slot_bytes > tail_bytes ? slot_bytes : tail_bytes)); // [F/2][MAGS]
     int* beat_h = reinterpret_cast<int*>(mags + (F / 2) * MAGS);    // [F][4]
 
@@ -202,37 +206,41 @@ __global__ void __launch_bounds__(RdifShape<N, F>::THREADS, MINB) stft_bars_rdif
         for (int r = 1; r < 16; r++) twc[r] = __ldg(p.twm + j * r);
     }
 
-    // Samples of the NEXT tile are fetched (raw int16) while the current tile's tail runs, so pass A
-    // never waits on global memory.  xraw is live across the tail only.
-    int xraw[NX];
-    auto fetch = [&](long long tile) {
-        const int ch = (int)(tile / p.tiles_per_channel);
-        const long long f0 = p.frame0 + (tile % p.tiles_per_channel) * F;
-        const long long s0 = f0 * (long long)p.hop;
-        const int16_t* xp = p.pcm + (long long)ch * p.channel_stride + s0 + t;
-        if (s0 + (long long)NX * M <= p.samples) {
-#pragma unroll
-            for (int r = 0; r < NX; r++) xraw[r] = xp[r * M];
-        } else {
-#pragma unroll
-            for (int r = 0; r < NX; r++) xraw[r] = (s0 + t + (long long)r * M < p.samples) ? (int)xp[r * M] : 0;
+    long long prev_f0 = -1; // tile whose band energy / bass are still to be written (after the next barrier)
+    int prev_ch = 0;
+    auto flush_aux = [&]() {
+        if (t < F && p.aux_w && prev_f0 >= 0) {
+            const long long fr = prev_f0 + t;
+            if (fr < p.frame_end) {
+                const int* h4 = beat_h + 4 * t;
+                int sum = wrap_add(wrap_add(h4[0], h4[1]), wrap_add(h4[2], h4[3]));
+                const float2 mb = mags[(t >> 1) * MAGS + pad_index(p.bass_bin)];
+                long long o = (long long)prev_ch * p.nf_aux + (fr - p.aux_base);
+                p.aux_w[o] = sum / 4;                                              // fft_lines.c:281
+                p.aux_bass[o] = trunc_i32((t & 1) ? mb.y : mb.x, p.strict);        // beatDetector.c:53
+            }
         }
     };
-#ifdef FFTL_REG_PREFETCH
-    if ((long long)blockIdx.x < p.total_tiles) fetch(blockIdx.x);
-#endif
 
     for (long long tile = blockIdx.x; tile < p.total_tiles; tile += gridDim.x) {
         const int ch = (int)(tile / p.tiles_per_channel);
         const long long f0 = p.frame0 + (tile % p.tiles_per_channel) * F; // first frame of the tile (even)
+        const long long s0 = f0 * (long long)p.hop;                      // its first sample
+        const int16_t* xp = p.pcm + (long long)ch * p.channel_stride + s0 + t;
 
         // ================= pass A =================
-#ifndef FFTL_REG_PREFETCH
-        fetch(tile);
-#endif
         float xr[NX];
+        if (s0 + (long long)NX * M <= p.samples) {
 #pragma unroll
-        for (int r = 0; r < NX; r++) xr[r] = (float)xraw[r];
+            for (int r = 0; r < NX; r++) xr[r] = (float)xp[r * M];
+        } else {
+#pragma unroll
+            for (int r = 0; r < NX; r++) xr[r] = (s0 + t + (long long)r * M < p.samples) ? (float)xp[r * M] : 0.0f;
+        }
+        if (!late_alias) {
+            __syncthreads(); // previous tile's tail is done with the aliased slots and has published beat_h
+            flush_aux();
+        }
         if (!RESIDENT) {
             if (WINDOWED) {
 #pragma unroll
@@ -243,6 +251,10 @@ __global__ void __launch_bounds__(RdifShape<N, F>::THREADS, MINB) stft_bars_rdif
         }
 #pragma unroll
         for (int pr = 0; pr < F / 2; pr++) {
+            if (late_alias && pr == F / 2 - 1) {
+                __syncthreads(); // previous tile's tail is done with the last pair's slots and has published beat_h
+                flush_aux();
+            }
             float2* ps = slots + pr * 16 * SLOT + pad_index(t);
             float y0[2], y8[2];
 #pragma unroll
@@ -324,22 +336,6 @@ __global__ void __launch_bounds__(RdifShape<N, F>::THREADS, MINB) stft_bars_rdif
             }
         }
         __syncthreads();
-#ifdef FFTL_REG_PREFETCH
-        if (tile + gridDim.x < p.total_tiles) fetch(tile + gridDim.x);
-#endif
-#ifdef FFTL_L2_PREFETCH
-        if (tile + gridDim.x < p.total_tiles) {
-            const long long nt = tile + gridDim.x;
-            const int nch = (int)(nt / p.tiles_per_channel);
-            const long long ns0 = (p.frame0 + (nt % p.tiles_per_channel) * F) * (long long)p.hop;
-            const int16_t* np_ = p.pcm + (long long)nch * p.channel_stride + ns0 + t;
-            if (ns0 + (long long)NX * M <= p.samples) {
-#pragma unroll
-                for (int r = 0; r < NX; r++) asm volatile("prefetch.global.L2 [%0];" ::"l"(np_ + r * M));
-            }
-        }
-#endif
-
         // ================= bins -> bars, SG, outputs: every item carries the tile's F frames =================
         // segments are at most 8 bins long and never cross a multiple of 16, so a segment is 8 consecutive
         // padded positions at most
@@ -423,23 +419,13 @@ __global__ void __launch_bounds__(RdifShape<N, F>::THREADS, MINB) stft_bars_rdif
                 }
             }
         }
-        // segsum/raw alias the slots the next tile's pass A is about to overwrite; the same barrier
-        // publishes beat_h
-        __syncthreads();
-        if (t < F && p.aux_w) {
-            const long long fr = f0 + t;
-            if (fr < p.frame_end) {
-                const int* h4 = beat_h + 4 * t;
-                int sum = wrap_add(wrap_add(h4[0], h4[1]), wrap_add(h4[2], h4[3]));
-                const float2 mb = mags[(t >> 1) * MAGS + pad_index(p.bass_bin)];
-                long long o = (long long)ch * p.nf_aux + (fr - p.aux_base);
-                p.aux_w[o] = sum / 4;                                              // fft_lines.c:281
-                p.aux_bass[o] = trunc_i32((t & 1) ? mb.y : mb.x, p.strict);        // beatDetector.c:53
-            }
-        }
-        // beat_h and mags are rewritten only after later barriers of the next tile, which these threads
-        // reach after the reads above.
+        // No barrier here: the next tile's pass A starts at once; the barrier that protects the aliased
+        // buffers and publishes beat_h is the one inside (late_alias) or in front of (otherwise) its pass A.
+        prev_f0 = f0;
+        prev_ch = ch;
     }
+    __syncthreads();
+    flush_aux();
 }
 
 } // namespace fftl

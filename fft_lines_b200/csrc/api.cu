@@ -460,7 +460,7 @@ static cudaError_t launch_rdif(const fftl_stft* h, RdifParams p, int channels, c
 {
     constexpr int MINB = 2; // two CTAs per SM is the design point (128 registers, ~105 KB shared memory)
     using Sh = RdifShape<4096, F>;
-    size_t smem = Sh::smem_bytes(p.bars_n, p.nseg);
+    size_t smem = Sh::smem_bytes(p.bars_n, p.nseg, p.sg_half);
     if ((smem + 1024) * MINB > 228 * 1024) return cudaErrorNotSupported;
     p.tiles_per_channel = (p.frame_end - p.frame0 + F - 1) / F;
     p.total_tiles = p.tiles_per_channel * channels;

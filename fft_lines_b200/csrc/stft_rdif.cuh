@@ -99,6 +99,17 @@ template <int N, int F> struct RdifShape {
     // even banks, the other half-warp (odd frame) the odd ones
     static constexpr int MAGS = padded_size(NB) + 3;
     __host__ __device__ static size_t tail_bytes(int bars, int nseg) { return (size_t)(nseg + bars) * F * sizeof(float); }
+    // per-CTA copies of the tail's tables (the L1 is tiny next to 105 KB of shared memory and is
+    // streamed through by the PCM, so table loads from global would pay L2 latency in every tail phase)
+    __host__ __device__ static size_t table_bytes(int bars, int nseg, int sg_half)
+    {
+        int m = 2 * sg_half + 1;
+        return (size_t)nseg * sizeof(int2) + (size_t)(bars + 1) * sizeof(int) + (size_t)bars * sizeof(float) + (size_t)m * m * sizeof(float);
+    }
+    static size_t smem_bytes(int bars, int nseg, int sg_half)
+    {
+        return smem_bytes(bars, nseg) + table_bytes(bars, nseg, sg_half) + 16;
+    }
     static size_t smem_bytes(int bars, int nseg)
     {
         // segment sums and raw bars alias the slot area (dead once pass B/C is done)
@@ -138,14 +149,14 @@ __device__ __forceinline__ float2 ldg_pinned(const float2* p)
 
 // Savitzky-Golay over the raw bar vector for F frames at once; TAPS < 0: run-time width.
 template <int F, int TAPS>
-__device__ __forceinline__ void sg_apply(const float* __restrict__ cf, const float* rw, int m, float* y)
+__device__ __forceinline__ void sg_apply(const float* cf, const float* rw, int m, float* y)
 {
 #pragma unroll
     for (int f = 0; f < F; f++) y[f] = 0.0f;
     if (TAPS > 0) {
 #pragma unroll
         for (int k = 0; k < TAPS; k++) {
-            const float c = __ldg(cf + k);
+            const float c = cf[k];
             float u[F];
             FrameVec<F>::load(rw + k * F, u);
 #pragma unroll
@@ -154,7 +165,7 @@ __device__ __forceinline__ void sg_apply(const float* __restrict__ cf, const flo
     } else {
 #pragma unroll 1
         for (int k = 0; k < m; k++) {
-            const float c = __ldg(cf + k);
+            const float c = cf[k];
             float u[F];
             FrameVec<F>::load(rw + k * F, u);
 #pragma unroll
@@ -185,6 +196,18 @@ __global__ void __launch_bounds__(RdifShape<N, F>::THREADS, MINB) stft_bars_rdif
     float* raw = segsum + p.nseg * F;                               // [bars][F]
     float2* mags = reinterpret_cast<float2*>(reinterpret_cast<char*>(smem) + (slot_bytes > tail_bytes ? slot_bytes : tail_bytes)); // [F/2][MAGS]
     int* beat_h = reinterpret_cast<int*>(mags + (F / 2) * MAGS);    // [F][4]
+    int2* t_seg = reinterpret_cast<int2*>(beat_h + F * 4);          // [nseg] (first bin, count)
+    int* t_bar0 = reinterpret_cast<int*>(t_seg + p.nseg);           // [bars+1]
+    float* t_inv = reinterpret_cast<float*>(t_bar0 + p.bars_n + 1); // [bars]
+    float* t_sg = t_inv + p.bars_n;                                 // [(2w+1)^2]
+    for (int i = threadIdx.x; i < p.nseg; i += M) {
+        const int l = __ldg(p.seg_lo + i);
+        t_seg[i] = make_int2(pad_index(l), __ldg(p.seg_hi + i) - l);
+    }
+    for (int i = threadIdx.x; i <= p.bars_n; i += M) t_bar0[i] = __ldg(p.bar_seg0 + i);
+    for (int i = threadIdx.x; i < p.bars_n; i += M) t_inv[i] = __ldg(p.bar_inv + i);
+    for (int i = threadIdx.x; i < (2 * p.sg_half + 1) * (2 * p.sg_half + 1); i += M) t_sg[i] = p.sg ? __ldg(p.sg + i) : 0.0f;
+    __syncthreads();
 
     const int t = threadIdx.x;
     const int B = p.bars_n;
@@ -340,8 +363,9 @@ __global__ void __launch_bounds__(RdifShape<N, F>::THREADS, MINB) stft_bars_rdif
         // segments are at most 8 bins long and never cross a multiple of 16, so a segment is 8 consecutive
         // padded positions at most
         for (int sgi = t; sgi < p.nseg; sgi += M) {
-            const int l = __ldg(p.seg_lo + sgi), cnt = __ldg(p.seg_hi + sgi) - l;
-            const float2* m0 = mags + pad_index(l);
+            const int2 sd = t_seg[sgi];
+            const int cnt = sd.y;
+            const float2* m0 = mags + sd.x;
             float acc[F];
 #pragma unroll
             for (int f = 0; f < F; f++) acc[f] = 0.0f;
@@ -360,7 +384,7 @@ __global__ void __launch_bounds__(RdifShape<N, F>::THREADS, MINB) stft_bars_rdif
         }
         __syncthreads();
         for (int b = t; b < B; b += M) {
-            const int a = __ldg(p.bar_seg0 + b), e = __ldg(p.bar_seg0 + b + 1);
+            const int a = t_bar0[b], e = t_bar0[b + 1];
             float acc[F];
             FrameVec<F>::load(segsum + a * F, acc);
             for (int k = a + 1; k < e; k++) {
@@ -369,7 +393,7 @@ __global__ void __launch_bounds__(RdifShape<N, F>::THREADS, MINB) stft_bars_rdif
 #pragma unroll
                 for (int f = 0; f < F; f++) acc[f] += u[f];
             }
-            const float inv = __ldg(p.bar_inv + b);
+            const float inv = t_inv[b];
 #pragma unroll
             for (int f = 0; f < F; f++) acc[f] *= inv;
             FrameVec<F>::store(raw + b * F, acc);
@@ -392,7 +416,7 @@ __global__ void __launch_bounds__(RdifShape<N, F>::THREADS, MINB) stft_bars_rdif
                     if (b < w) { row = b; base = 0; }
                     else if (b >= B - w) { row = m - (B - b); base = B - m; }
                     else { row = w; base = b - w; }
-                    sg_apply<F, (SGW > 0 ? 2 * SGW + 1 : -1)>(p.sg + row * m, raw + base * F, m, y);
+                    sg_apply<F, (SGW > 0 ? 2 * SGW + 1 : -1)>(t_sg + row * m, raw + base * F, m, y);
                 }
                 float* ob = p.bars + (o0 + b);
 #pragma unroll

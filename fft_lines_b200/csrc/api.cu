@@ -205,10 +205,14 @@ template <int N> static cudaError_t launch_stft(const StftParams& p, int channel
         cudaError_t e = cudaFuncSetAttribute(stft_bars_kernel<N>, cudaFuncAttributeMaxDynamicSharedMemorySize, (int)smem);
         if (e != cudaSuccess) return e;
     }
-    long long blocks = (pairs + Sh::PAIRS - 1) / Sh::PAIRS;
+    // pairs of all channels are numbered consecutively, so many-channel / few-frame jobs still fill CTAs
+    long long blocks = (pairs * channels + Sh::PAIRS - 1) / Sh::PAIRS;
     if (blocks <= 0) return cudaSuccess;
-    dim3 grid((unsigned)blocks, (unsigned)channels);
-    stft_bars_kernel<N><<<grid, Sh::THREADS, smem, st>>>(p);
+    if (blocks > 0x7fffffffll) return cudaErrorInvalidValue;
+    StftParams q = p;
+    q.pairs_per_channel = pairs;
+    q.channels = channels;
+    stft_bars_kernel<N><<<(unsigned)blocks, Sh::THREADS, smem, st>>>(q);
     return cudaGetLastError();
 }
 
@@ -645,11 +649,19 @@ extern "C" int fftl_stft_run_device(fftl_stft* h, const int16_t* pcm, int32_t ch
             if (rc) return rc;
         }
     }
-    cudaEvent_t* evs = h->ev[h->timing_next];
+    // inside a CUDA-graph capture the timing events are skipped (they could not be queried afterwards)
+    cudaStreamCaptureStatus cap = cudaStreamCaptureStatusNone;
+    if (cudaStreamIsCapturing(st, &cap) != cudaSuccess) {
+        cudaGetLastError();
+        cap = cudaStreamCaptureStatusNone;
+    }
+    cudaEvent_t* evs = (cap == cudaStreamCaptureStatusNone) ? h->ev[h->timing_next] : nullptr;
     rc = run_range(h, pcm, channels, cstride, sstride, samples, fftl_stft_num_frames(h, samples), warm, fb, fe, fb, fe - fb, warm, nf_aux, bars, bars_i32, beat != nullptr, beat, st, evs);
     if (rc) return rc;
-    h->timing_next = (h->timing_next + 1) % TIMING_SLOTS;
-    if (h->timing_count < TIMING_SLOTS) h->timing_count++;
+    if (evs) {
+        h->timing_next = (h->timing_next + 1) % TIMING_SLOTS;
+        if (h->timing_count < TIMING_SLOTS) h->timing_count++;
+    }
     return FFTL_OK;
 }
 
@@ -707,7 +719,8 @@ extern "C" int fftl_stft_run(fftl_stft* h, const int16_t* pcm, int32_t channels,
         if (rc) return rc;
     }
     // chunk size: ~64 MiB of bar output per slot, at least 512 frames, even
-    int64_t chunk = (int64_t)(64ll << 20) / ((int64_t)channels * B * 4);
+    static const long long chunk_mib = getenv("FFTL_CHUNK_MIB") ? atoll(getenv("FFTL_CHUNK_MIB")) : 64; // developer knob
+    int64_t chunk = (int64_t)(chunk_mib << 20) / ((int64_t)channels * B * 4);
     if (chunk < 512) chunk = 512;
     if (chunk > fe - warm) chunk = fe - warm;
     chunk += chunk & 1;
@@ -738,8 +751,9 @@ extern "C" int fftl_stft_run(fftl_stft* h, const int16_t* pcm, int32_t channels,
         if (interleaved) {
             CUDA_TRY(cudaMemcpyAsync(d_pcm, pcm + s0 * channels, pcm_bytes, cudaMemcpyHostToDevice, h->s_h2d));
         } else {
-            for (int ch = 0; ch < channels; ch++)
-                CUDA_TRY(cudaMemcpyAsync(d_pcm + (size_t)ch * span, pcm + ch * cstride + s0, sizeof(int16_t) * span, cudaMemcpyHostToDevice, h->s_h2d));
+            // one strided copy for all channels (1024 streams must not become 1024 memcpy calls)
+            CUDA_TRY(cudaMemcpy2DAsync(d_pcm, sizeof(int16_t) * span, pcm + s0, sizeof(int16_t) * cstride, sizeof(int16_t) * span,
+                                       (size_t)channels, cudaMemcpyHostToDevice, h->s_h2d));
         }
         CUDA_TRY(cudaEventRecord(h->ev_h2d[slot], h->s_h2d));
         CUDA_TRY(cudaStreamWaitEvent(h->stream, h->ev_h2d[slot], 0));
@@ -763,16 +777,16 @@ extern "C" int fftl_stft_run(fftl_stft* h, const int16_t* pcm, int32_t channels,
         // slot's pcm until this compute is done -> h2d stream waits on ev_comp of the slot it reuses
         CUDA_TRY(cudaStreamWaitEvent(h->s_h2d, h->ev_comp[slot ^ 1], 0));
         if (ne > 0) {
-            for (int ch = 0; ch < channels; ch++) {
-                size_t off_h = ((size_t)ch * nf_total + (size_t)(ea - fb)) * B;
-                size_t off_d = (size_t)ch * ne * B;
-                CUDA_TRY(cudaMemcpyAsync(bars + off_h, (float*)h->d_stage[slot][1] + off_d, sizeof(float) * ne * B, cudaMemcpyDeviceToHost, h->s_d2h));
-                if (bars_i32)
-                    CUDA_TRY(cudaMemcpyAsync(bars_i32 + off_h, (int32_t*)h->d_stage[slot][2] + off_d, sizeof(int32_t) * ne * B, cudaMemcpyDeviceToHost, h->s_d2h));
-                if (beat)
-                    CUDA_TRY(cudaMemcpyAsync(beat + (size_t)ch * nf_total + (ea - fb), (fftl_beat*)h->d_stage[slot][3] + (size_t)ch * ne,
-                                             sizeof(fftl_beat) * ne, cudaMemcpyDeviceToHost, h->s_d2h));
-            }
+            // host [ch][nf_total][B] <- device [ch][ne][B]: one strided copy per output
+            const size_t off_h = (size_t)(ea - fb) * B;
+            CUDA_TRY(cudaMemcpy2DAsync(bars + off_h, sizeof(float) * nf_total * B, h->d_stage[slot][1], sizeof(float) * ne * B,
+                                       sizeof(float) * ne * B, (size_t)channels, cudaMemcpyDeviceToHost, h->s_d2h));
+            if (bars_i32)
+                CUDA_TRY(cudaMemcpy2DAsync(bars_i32 + off_h, sizeof(int32_t) * nf_total * B, h->d_stage[slot][2], sizeof(int32_t) * ne * B,
+                                           sizeof(int32_t) * ne * B, (size_t)channels, cudaMemcpyDeviceToHost, h->s_d2h));
+            if (beat)
+                CUDA_TRY(cudaMemcpy2DAsync(beat + (ea - fb), sizeof(fftl_beat) * nf_total, h->d_stage[slot][3], sizeof(fftl_beat) * ne,
+                                           sizeof(fftl_beat) * ne, (size_t)channels, cudaMemcpyDeviceToHost, h->s_d2h));
         }
         CUDA_TRY(cudaEventRecord(h->ev_d2h[slot], h->s_d2h));
     }

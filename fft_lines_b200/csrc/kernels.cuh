@@ -46,6 +46,8 @@ struct StftParams {
     long long nf_emit;     // frame_end - frame_emit   (output stride per channel)
     long long nf_aux;      // aux stride per channel
     long long aux_base;    // aux index of frame0 is (frame0 - aux_base)
+    long long pairs_per_channel;
+    int channels;
     const float* window;   // n floats or nullptr (RECT)
     const float2* tw;      // W_n^m
     const int* lo;
@@ -84,11 +86,13 @@ __global__ void __launch_bounds__(StftShape<N>::THREADS) stft_bars_kernel(const 
     int* beat_h = reinterpret_cast<int*>(reinterpret_cast<float*>(smem + PAIRS * padded_size(N)) + PAIRS * 2 * B) + pic * 8;
     auto sync = [] { __syncthreads(); };
 
-    const long long pair = (long long)blockIdx.x * PAIRS + pic;
-    const int ch = blockIdx.y;
+    const long long gpair = (long long)blockIdx.x * PAIRS + pic;        // pair index over all channels
+    const bool live = gpair < p.pairs_per_channel * p.channels;
+    const int ch = live ? (int)(gpair / p.pairs_per_channel) : 0;
+    const long long pair = live ? gpair - (long long)ch * p.pairs_per_channel : 0;
     const long long fa = p.frame0 + 2 * pair;
-    const bool va = fa < p.frame_end, vb = fa + 1 < p.frame_end;       // produce outputs for
-    const bool la = fa < p.frames_total, lb = fa + 1 < p.frames_total; // samples exist for
+    const bool va = live && fa < p.frame_end, vb = live && fa + 1 < p.frame_end;       // produce outputs for
+    const bool la = live && fa < p.frames_total, lb = live && fa + 1 < p.frames_total; // samples exist for
     const int16_t* xa = p.pcm + ch * p.channel_stride + fa * p.hop * p.sample_stride;
     const long long ss = p.sample_stride;
     const long long hs = (long long)p.hop * ss;

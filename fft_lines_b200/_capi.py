@@ -13,6 +13,7 @@ FFTL_OK, FFTL_ERR_ARG, FFTL_ERR_CUDA, FFTL_ERR_NOMEM, FFTL_ERR_STATE = 0, 1, 2, 
 WINDOW_RECT, WINDOW_HANN = 0, 1
 BINNING_LINEAR, BINNING_LOG = 0, 1
 BEAT_SAMPLES, TEMPO_RING = 160, 256
+MOVE_EXACT, MOVE_REFERENCE = 0, 1
 
 
 class FftlConfig(C.Structure):
@@ -46,7 +47,8 @@ EXPORTED_FUNCTIONS = {
         "fftl_config_reference", "fftl_config_extended", "fftl_config_validate", "fftl_build_bins",
         "fftl_build_sg", "fftl_stft_create", "fftl_stft_destroy", "fftl_stft_num_frames",
         "fftl_stft_run_device", "fftl_stft_run", "fftl_stft_launch_count", "fftl_stft_timing",
-        "fftl_host_alloc", "fftl_host_free", "fftl_synth_pcm_device", "fftl_measure_fp32_peak", "fftl_last_error",
+        "fftl_stream_create", "fftl_stream_destroy", "fftl_stream_reset", "fftl_stream_push_device",
+        "fftl_stream_push", "fftl_stream_launch_count", "fftl_host_alloc", "fftl_host_free", "fftl_synth_pcm_device", "fftl_measure_fp32_peak", "fftl_last_error",
         "fftl_last_error_string", "fftl_clear_error", "fftl_version", "fftl_device_count",
         "fftl_set_n", "fftl_get_n", "fftl_compat_reset_beat", "fftl_compat_launch_count",
     ],
@@ -95,6 +97,14 @@ def lib():
     L.fftl_stft_launch_count.argtypes = [vp]
     L.fftl_stft_launch_count.restype = C.c_int64
     L.fftl_stft_timing.argtypes = [vp, i32p, f32p, f32p]
+    L.fftl_stream_create.argtypes = [cfgp, C.c_int32, C.c_int32, C.c_int, C.POINTER(vp)]
+    L.fftl_stream_destroy.argtypes = [vp]
+    L.fftl_stream_destroy.restype = None
+    L.fftl_stream_reset.argtypes = [vp]
+    L.fftl_stream_push_device.argtypes = [vp, vp, C.c_int32, C.c_int64, vp, vp, vp, vp]
+    L.fftl_stream_push.argtypes = [vp, vp, C.c_int32, C.c_int64, vp, vp, vp]
+    L.fftl_stream_launch_count.argtypes = [vp]
+    L.fftl_stream_launch_count.restype = C.c_int64
     L.fftl_host_alloc.argtypes = [C.c_uint64]
     L.fftl_host_alloc.restype = vp
     L.fftl_host_free.argtypes = [vp]

@@ -14,6 +14,7 @@
 
 #include "kernels.cuh"
 #include "stft_rdif.cuh"
+#include "stream.cuh"
 #include "../../include/fft_calculate.h"
 #include "../../include/beatDetector.h"
 
@@ -545,7 +546,7 @@ static cudaError_t try_rdif(const fftl_stft* h, const StftParams& q, int channel
 // starts computing aux (frames before it must already be in the aux arrays).
 static int run_range(fftl_stft* h, const int16_t* pcm, int channels, int64_t cstride, int64_t sstride, int64_t samples, int64_t frames_total, int64_t compute_from,
                      int64_t fb, int64_t fe, int64_t out_base, int64_t nf_emit, int64_t aux_base, int64_t nf_aux, float* bars,
-                     int32_t* bars_i32, bool aux, fftl_beat* beat, cudaStream_t st, cudaEvent_t* evs)
+                     int32_t* bars_i32, bool aux, fftl_beat* beat, cudaStream_t st, cudaEvent_t* evs, bool force_generic = false)
 {
     const fftl_config& c = h->cfg;
     StftParams p;
@@ -580,7 +581,7 @@ static int run_range(fftl_stft* h, const int16_t* pcm, int channels, int64_t cst
     p.circle_add = c.circle ? 10.0f : 0.0f; // fft_lines.c:204-207
     long long pairs = (fe - compute_from + 1) / 2;
     if (evs) CUDA_TRY(cudaEventRecord(evs[0], st));
-    cudaError_t fe_ = try_rdif(h, p, channels, samples, st);
+    cudaError_t fe_ = force_generic ? cudaErrorNotSupported : try_rdif(h, p, channels, samples, st);
     if (fe_ == cudaErrorNotSupported) {
         CUDA_TRY(dispatch_stft(c.n, p, channels, pairs, st)); // generic kernel: any n, strided PCM, any hop
     } else {
@@ -793,6 +794,171 @@ extern "C" int fftl_stft_run(fftl_stft* h, const int16_t* pcm, int32_t channels,
     CUDA_TRY(cudaStreamSynchronize(h->s_d2h));
     CUDA_TRY(cudaStreamSynchronize(h->stream));
     CUDA_TRY(cudaStreamSynchronize(h->s_h2d));
+    return FFTL_OK;
+}
+
+// ------------------------------------------------------------------ streams
+struct fftl_stream {
+    fftl_stft* core;        // tables, launcher, aux (w, bass) buffers
+    int streams, move_mode;
+    int16_t* d_window;      // [streams][n]
+    int* d_w_ring;          // [streams][160]
+    int* d_w_sum;           // [streams]
+    int* d_tempo_ring;      // [streams][256]
+    StreamState* d_state;
+    // staging for the host-buffer variant
+    int16_t* d_fresh;
+    size_t fresh_cap;
+    float* d_bars;
+    int32_t* d_bars_i32;
+    fftl_beat* d_beat;
+    int64_t launches;
+};
+
+extern "C" void fftl_stream_destroy(fftl_stream* s)
+{
+    if (!s) return;
+    if (s->core) {
+        cudaSetDevice(s->core->device);
+        cudaStreamSynchronize(s->core->stream);
+    }
+    cudaFree(s->d_window);
+    cudaFree(s->d_w_ring);
+    cudaFree(s->d_w_sum);
+    cudaFree(s->d_tempo_ring);
+    cudaFree(s->d_state);
+    cudaFree(s->d_fresh);
+    cudaFree(s->d_bars);
+    cudaFree(s->d_bars_i32);
+    cudaFree(s->d_beat);
+    cudaGetLastError();
+    fftl_stft_destroy(s->core);
+    free(s);
+}
+
+extern "C" int fftl_stream_reset(fftl_stream* s)
+{
+    if (!s) return set_error(FFTL_ERR_ARG, "stream handle is NULL");
+    CUDA_TRY(cudaSetDevice(s->core->device));
+    const size_t S = (size_t)s->streams;
+    CUDA_TRY(cudaMemset(s->d_window, 0, sizeof(int16_t) * S * s->core->cfg.n));
+    CUDA_TRY(cudaMemset(s->d_w_ring, 0, sizeof(int) * S * FFTL_BEAT_SAMPLES));
+    CUDA_TRY(cudaMemset(s->d_w_sum, 0, sizeof(int) * S));
+    CUDA_TRY(cudaMemset(s->d_tempo_ring, 0, sizeof(int) * S * FFTL_TEMPO_RING));
+    CUDA_TRY(cudaMemset(s->d_state, 0, sizeof(StreamState)));
+    return FFTL_OK;
+}
+
+extern "C" int fftl_stream_create(const fftl_config* cfg, int32_t streams, int32_t move_mode, int device, fftl_stream** out)
+{
+    if (!out) return set_error(FFTL_ERR_ARG, "out is NULL");
+    *out = nullptr;
+    if (streams < 1 || streams > (1 << 22)) return set_error(FFTL_ERR_ARG, "streams=%d out of range", streams);
+    if (move_mode != FFTL_MOVE_EXACT && move_mode != FFTL_MOVE_REFERENCE) return set_error(FFTL_ERR_ARG, "unknown move_mode %d", move_mode);
+    fftl_stream* s = (fftl_stream*)calloc(1, sizeof(fftl_stream));
+    if (!s) return set_error(FFTL_ERR_NOMEM, "out of host memory");
+    int rc = fftl_stft_create(cfg, device, &s->core);
+    if (rc) {
+        free(s);
+        return rc;
+    }
+    s->streams = streams;
+    s->move_mode = move_mode;
+    const size_t S = (size_t)streams;
+    const int B = cfg->bars;
+    cudaError_t e = cudaSuccess;
+    if (e == cudaSuccess) e = cudaMalloc(&s->d_window, sizeof(int16_t) * S * cfg->n);
+    if (e == cudaSuccess) e = cudaMalloc(&s->d_w_ring, sizeof(int) * S * FFTL_BEAT_SAMPLES);
+    if (e == cudaSuccess) e = cudaMalloc(&s->d_w_sum, sizeof(int) * S);
+    if (e == cudaSuccess) e = cudaMalloc(&s->d_tempo_ring, sizeof(int) * S * FFTL_TEMPO_RING);
+    if (e == cudaSuccess) e = cudaMalloc(&s->d_state, sizeof(StreamState));
+    if (e == cudaSuccess) e = cudaMalloc(&s->d_bars, sizeof(float) * S * B);
+    if (e == cudaSuccess) e = cudaMalloc(&s->d_bars_i32, sizeof(int32_t) * S * B);
+    if (e == cudaSuccess) e = cudaMalloc(&s->d_beat, sizeof(fftl_beat) * S);
+    void* pv = s->core->d_aux;
+    if (e == cudaSuccess && ensure_bytes(&pv, &s->core->aux_capacity, sizeof(int) * 2 * S)) e = cudaErrorMemoryAllocation;
+    s->core->d_aux = (int*)pv;
+    if (e != cudaSuccess) {
+        set_error(FFTL_ERR_NOMEM, "stream state allocation failed: %s", cudaGetErrorString(e));
+        fftl_stream_destroy(s);
+        return FFTL_ERR_NOMEM;
+    }
+    rc = fftl_stream_reset(s);
+    if (rc) {
+        fftl_stream_destroy(s);
+        return rc;
+    }
+    *out = s;
+    return FFTL_OK;
+}
+
+extern "C" int64_t fftl_stream_launch_count(const fftl_stream* s) { return s ? s->launches : 0; }
+
+extern "C" int fftl_stream_push_device(fftl_stream* s, const int16_t* fresh, int32_t count, int64_t stride, float* bars, int32_t* bars_i32,
+                                       fftl_beat* beat, void* cuda_stream)
+{
+    if (!s) return set_error(FFTL_ERR_ARG, "stream handle is NULL");
+    if (!fresh || !bars) return set_error(FFTL_ERR_ARG, "fresh and bars must not be NULL");
+    if (count < 1) return set_error(FFTL_ERR_ARG, "count=%d: a push needs at least one new sample", count);
+    fftl_stft* h = s->core;
+    const fftl_config& c = h->cfg;
+    CUDA_TRY(cudaSetDevice(h->device));
+    cudaStream_t st = (cudaStream_t)cuda_stream;
+    const float dt = (float)count / c.sample_rate; // timeDelta of this tick (fft_lines.c:265 uses wall clock)
+    if (count > c.n) { // only the newest n samples can matter
+        if (s->move_mode == FFTL_MOVE_REFERENCE) return set_error(FFTL_ERR_ARG, "count > n is undefined for the reference's MoveArray");
+        fresh += count - c.n;
+        count = c.n;
+    }
+    stream_slide_kernel<<<s->streams, 256, 0, st>>>(s->d_window, fresh, c.n, count, stride, s->move_mode == FFTL_MOVE_REFERENCE);
+    CUDA_TRY(cudaGetLastError());
+    // one frame per stream: channels = streams, samples = n
+    int rc = run_range(h, s->d_window, s->streams, c.n, 1, c.n, 1, 0, 0, 1, 0, 1, 0, 1, bars, bars_i32, true, nullptr, st, nullptr, true);
+    if (rc) return rc;
+    StreamBeatParams bp;
+    bp.aux_w = h->d_aux;
+    bp.aux_bass = h->d_aux + s->streams;
+    bp.w_ring = s->d_w_ring;
+    bp.w_sum = s->d_w_sum;
+    bp.tempo_ring = s->d_tempo_ring;
+    bp.state = s->d_state;
+    bp.out = beat ? beat : s->d_beat;
+    bp.tw256 = h->d_tw256;
+    bp.streams = s->streams;
+    bp.n_times_dt = (float)c.n * dt;
+    bp.strict = c.strict_int;
+    stream_beat_kernel<<<(s->streams + 31) / 32, 256, 0, st>>>(bp);
+    CUDA_TRY(cudaGetLastError());
+    stream_tick_kernel<<<1, 1, 0, st>>>(s->d_state);
+    CUDA_TRY(cudaGetLastError());
+    s->launches += 4;
+    return FFTL_OK;
+}
+
+extern "C" int fftl_stream_push(fftl_stream* s, const int16_t* fresh, int32_t count, int64_t stride, float* bars, int32_t* bars_i32,
+                                fftl_beat* beat)
+{
+    if (!s) return set_error(FFTL_ERR_ARG, "stream handle is NULL");
+    if (!fresh || !bars) return set_error(FFTL_ERR_ARG, "fresh and bars must not be NULL");
+    if (count < 1) return set_error(FFTL_ERR_ARG, "count=%d: a push needs at least one new sample", count);
+    fftl_stft* h = s->core;
+    CUDA_TRY(cudaSetDevice(h->device));
+    const size_t S = (size_t)s->streams;
+    const int B = h->cfg.bars;
+    size_t need = sizeof(int16_t) * S * count;
+    void* pv = s->d_fresh;
+    if (s->fresh_cap < need) CUDA_TRY(cudaStreamSynchronize(h->stream));
+    int rc = ensure_bytes(&pv, &s->fresh_cap, need);
+    s->d_fresh = (int16_t*)pv;
+    if (rc) return rc;
+    CUDA_TRY(cudaMemcpy2DAsync(s->d_fresh, sizeof(int16_t) * count, fresh, sizeof(int16_t) * stride, sizeof(int16_t) * count, S,
+                               cudaMemcpyHostToDevice, h->stream));
+    rc = fftl_stream_push_device(s, s->d_fresh, count, count, s->d_bars, bars_i32 ? s->d_bars_i32 : nullptr, s->d_beat, h->stream);
+    if (rc) return rc;
+    CUDA_TRY(cudaMemcpyAsync(bars, s->d_bars, sizeof(float) * S * B, cudaMemcpyDeviceToHost, h->stream));
+    if (bars_i32) CUDA_TRY(cudaMemcpyAsync(bars_i32, s->d_bars_i32, sizeof(int32_t) * S * B, cudaMemcpyDeviceToHost, h->stream));
+    if (beat) CUDA_TRY(cudaMemcpyAsync(beat, s->d_beat, sizeof(fftl_beat) * S, cudaMemcpyDeviceToHost, h->stream));
+    CUDA_TRY(cudaStreamSynchronize(h->stream));
     return FFTL_OK;
 }
 

@@ -1,0 +1,202 @@
+// stream.cuh -- many-stream real-time front end (BASELINE configs[2]).
+//
+// The reference keeps ONE sliding window of the last N samples per channel
+// (GetAudioBuffer + MoveArray, fft_lines/wasapi_audio.cpp:390-484) and runs one
+// WM_TIMER tick on it (fft_lines.c:186-236, :281).  Here `streams` such windows
+// and their beat state live on the device; one push = one tick for every stream:
+//   stream_slide_kernel   MoveArray for all streams (exact, or with the reference's
+//                         off-by-one, wasapi_audio.cpp:394)
+//   stft_bars_kernel<N>   one frame per stream (kernels.cuh)
+//   stream_beat_kernel    AddBeatSample + BassBeatDetector on per-stream rings
+// All three take their positions from a device-resident tick counter, so the
+// triple can be captured once in a CUDA graph and replayed every tick.
+#pragma once
+#include "kernels.cuh"
+
+namespace fftl {
+
+struct StreamState {
+    long long tick;      // number of completed pushes
+};
+
+// window[s][0..n) <- shift by `count` (or count-1 in reference mode), append new[s][0..count)
+// One CTA per stream; the window is staged through registers so the shift is safe in place.
+__global__ void __launch_bounds__(256) stream_slide_kernel(int16_t* __restrict__ window, const int16_t* __restrict__ fresh, int n,
+                                                           int count, long long fresh_stride, int reference_move)
+{
+    const int s = blockIdx.x;
+    int16_t* w = window + (long long)s * n;
+    const int16_t* f = fresh + (long long)s * fresh_stride;
+    const int shift = reference_move ? count - 1 : count; // wasapi_audio.cpp:394 copies from k + addCount - 1
+    const int keep = n - count;                            // samples that survive (count <= n)
+    constexpr int PER = 64;                                // 256 threads * 64 = 16384 samples max
+    int16_t v[PER];
+#pragma unroll
+    for (int i = 0; i < PER; i++) {
+        int k = threadIdx.x + i * 256;
+        v[i] = (k < keep) ? w[k + shift] : (k < n ? f[k - keep] : (int16_t)0);
+    }
+    __syncthreads();
+#pragma unroll
+    for (int i = 0; i < PER; i++) {
+        int k = threadIdx.x + i * 256;
+        if (k < n) w[k] = v[i];
+    }
+}
+
+struct StreamBeatParams {
+    const int* aux_w;       // [streams] band energy of this tick
+    const int* aux_bass;    // [streams] (int)|X[bass_bin]| of this tick
+    int* w_ring;            // [streams][160]   beatValues   (beatDetector.c:14)
+    int* w_sum;             // [streams]        sumOfBeatValues
+    int* tempo_ring;        // [streams][256]   bassBeatBuffer (settingsFile.c:295)
+    StreamState* state;
+    fftl_beat* out;         // [streams]
+    const float2* tw256;
+    int streams;
+    float n_times_dt;       // (float)N * timeDelta of this tick
+    int strict;
+};
+
+// 32 streams per CTA: streams 2g, 2g+1 share one complex 256-point transform of their tempo rings.
+__global__ void __launch_bounds__(256) stream_beat_kernel(const StreamBeatParams p)
+{
+    __shared__ float2 s_tw[FFTL_TEMPO_RING];
+    __shared__ float2 sf[16][padded_size(FFTL_TEMPO_RING)];
+    const int tid = threadIdx.x;
+    const long long tick = p.state->tick;
+    const int pos256 = (int)(tick % FFTL_TEMPO_RING), pos160 = (int)(tick % FFTL_BEAT_SAMPLES);
+    s_tw[tid] = __ldg(p.tw256 + tid);
+    __syncthreads();
+    {
+        const int grp = tid >> 4, l = tid & 15;
+        const int sa = blockIdx.x * 32 + 2 * grp, sb = sa + 1;
+        const bool va = sa < p.streams, vb = sb < p.streams;
+        const int na = va ? p.aux_bass[sa] : 0, nb = vb ? p.aux_bass[sb] : 0;
+        int* ra = p.tempo_ring + (long long)sa * FFTL_TEMPO_RING;
+        int* rb = p.tempo_ring + (long long)sb * FFTL_TEMPO_RING;
+        float2 v[16];
+#pragma unroll
+        for (int r = 0; r < 16; r++) {
+            const int i = l + 16 * r;
+            int a = va ? ra[i] : 0, b = vb ? rb[i] : 0;
+            if (i == pos256) { // beatDetector.c:53: the new value goes in before the transform
+                a = na;
+                b = nb;
+                if (va) ra[i] = na;
+                if (vb) rb[i] = nb;
+            }
+            v[r] = make_float2((float)a, (float)b);
+        }
+        auto sync16 = [] { __syncwarp(); };
+        float2* s = sf[grp];
+        stockham_pass<256, 16, 1, 16, false>(v, s, s_tw, l, sync16);
+#pragma unroll
+        for (int r = 0; r < 16; r++) v[r] = s[pad_index(l + 16 * r)];
+#pragma unroll
+        for (int r = 1; r < 16; r++) v[r] = cmul(v[r], s_tw[l * r]);
+        Radix<16>::run(v);
+        __syncwarp();
+        const int src = (16 - l) & 15;
+        int* ha = reinterpret_cast<int*>(s);
+        int* hb = ha + BEAT_HBS;
+#pragma unroll
+        for (int kk = 0; kk <= 10; kk++) {
+            const int rr = 4 * (kk & 3) + (kk >> 2);
+            const int kp = 15 - kk, rp = 4 * (kp & 3) + (kp >> 2);
+            float pr_ = __shfl_sync(0xffffffffu, v[rp].x, src, 16);
+            float pi_ = __shfl_sync(0xffffffffu, v[rp].y, src, 16);
+            if (l == 0) {
+                const int ks = (16 - kk) & 15, rs = 4 * (ks & 3) + (ks >> 2);
+                pr_ = v[rs].x;
+                pi_ = v[rs].y;
+            }
+            float ar = v[rr].x + pr_, ai = v[rr].y - pi_;
+            float br = v[rr].x - pr_, bi = v[rr].y + pi_;
+            const int k = l + 16 * kk;
+            if (k <= FFTL_BEAT_SAMPLES) {
+                ha[k] = trunc_i32(0.5f * sqrtf(fmaf(ar, ar, ai * ai)), p.strict);
+                hb[k] = trunc_i32(0.5f * sqrtf(fmaf(br, br, bi * bi)), p.strict);
+            }
+        }
+    }
+    __syncthreads();
+    {
+        // peak scan, 8 lanes per stream (same code shape as beat_post_kernel)
+        const int si = tid >> 3, sub = tid & 7;
+        const int s = blockIdx.x * 32 + si;
+        const int* h = reinterpret_cast<const int*>(sf[si >> 1]) + (si & 1) * BEAT_HBS;
+        const int i0 = 20 * sub;
+        unsigned bits = 0;
+        int prev = (i0 == 0) ? 0 : h[i0 - 1];
+        int cur = h[i0];
+#pragma unroll
+        for (int q = 0; q < 20; q++) {
+            int nxt = h[i0 + q + 1];
+            int dold = (i0 + q == 0) ? 0 : wrap_sub(cur, prev);
+            int dnew = wrap_sub(nxt, cur);
+            if (dold >= 0 && dnew <= 0) bits |= 1u << q;
+            prev = cur;
+            cur = nxt;
+        }
+        int cnt = __popc(bits), incl = cnt;
+#pragma unroll
+        for (int o = 1; o < 8; o <<= 1) {
+            int n = __shfl_up_sync(0xffffffffu, incl, o, 8);
+            if (sub >= o) incl += n;
+        }
+        int rank = incl - cnt;
+        int best_val = 0, best_idx = -1;
+        int first = bits ? (i0 + __ffs(bits) - 1) : 1 << 30;
+        unsigned bb = bits;
+        while (bb) {
+            int q = __ffs(bb) - 1;
+            bb &= bb - 1;
+            int i = i0 + q;
+            int hv = h[i];
+            if (rank < 30 && i > 30 && hv > best_val) {
+                best_val = hv;
+                best_idx = i;
+            }
+            rank++;
+        }
+#pragma unroll
+        for (int o = 4; o > 0; o >>= 1) {
+            int ov = __shfl_xor_sync(0xffffffffu, best_val, o, 8);
+            int oi = __shfl_xor_sync(0xffffffffu, best_idx, o, 8);
+            int of = __shfl_xor_sync(0xffffffffu, first, o, 8);
+            bool take = (oi >= 0) && (best_idx < 0 || ov > best_val || (ov == best_val && oi < best_idx));
+            if (take) {
+                best_val = ov;
+                best_idx = oi;
+            }
+            first = of < first ? of : first;
+        }
+        if (sub == 0 && s < p.streams) {
+            const int peak = best_idx >= 0 ? best_idx : (first < (1 << 30) ? first : 0);
+            // AddBeatSample (beatDetector.c:30-44) on the stream's own ring
+            const int w = p.aux_w[s];
+            int* ring = p.w_ring + (long long)s * FFTL_BEAT_SAMPLES;
+            int sum = wrap_sub(wrap_add(p.w_sum[s], w), ring[pos160]);
+            ring[pos160] = w;
+            p.w_sum[s] = sum;
+            const int thr = sum / FFTL_BEAT_SAMPLES;
+            const float qv = __fdiv_rn((float)w, (float)thr);
+            fftl_beat rec;
+            rec.w = w;
+            rec.thr = thr;
+            rec.beat_value = trunc_i32(__fmul_rn(qv, 128.0f), 1);
+            rec.flag = (thr > 0 && w > thr) ? 1 : 0;
+            rec.bass = p.aux_bass[s];
+            rec.peak_index = peak;
+            rec.movement_per_sec = __fmul_rn(p.n_times_dt, (float)peak);
+            rec.reserved = 0;
+            p.out[s] = rec;
+        }
+    }
+}
+
+// advances the tick once per push, after every block of stream_beat_kernel has read it
+__global__ void stream_tick_kernel(StreamState* st) { st->tick++; }
+
+} // namespace fftl

@@ -141,6 +141,29 @@ int64_t fftl_stft_launch_count(const fftl_stft* h);
  * Waits for those calls to finish. */
 int fftl_stft_timing(fftl_stft* h, int32_t* calls, float* total_ms, float* bars_kernel_ms);
 
+/* ---- many-stream real-time front end ------------------------------------
+ * `streams` sliding windows of the last n samples and their beat state live on
+ * the device; one push = one tick of the reference's WM_TIMER for every stream:
+ * GetAudioBuffer/MoveArray (wasapi_audio.cpp:390-484: shift the window, append
+ * the new samples), then the spectrum chain and AddBeatSample/BassBeatDetector
+ * on the stream's own rings (fft_lines.c:186-236, :281).  timeDelta of a tick is
+ * count/sample_rate.  cfg->hop is ignored (count is the hop, it may vary).     */
+enum { FFTL_MOVE_EXACT = 0,      /* window = previous window shifted by count, new samples appended           */
+       FFTL_MOVE_REFERENCE = 1   /* the reference's MoveArray shifts by count-1 (wasapi_audio.cpp:394): the
+                                    newest old sample is dropped on every push                                 */ };
+typedef struct fftl_stream fftl_stream;
+int  fftl_stream_create(const fftl_config* cfg, int32_t streams, int32_t move_mode, int device, fftl_stream** out);
+void fftl_stream_destroy(fftl_stream* s);
+int  fftl_stream_reset(fftl_stream* s);      /* windows, rings and tick counter back to zero */
+/* fresh: [streams][count] int16 with row stride `stream_stride` (1 <= count).  Outputs: bars [streams][bars],
+ * bars_i32 (may be NULL), beat [streams] (may be NULL).  Device variant is asynchronous on cuda_stream and can
+ * be captured in a CUDA graph (all positions come from a device-resident tick counter).                       */
+int  fftl_stream_push_device(fftl_stream* s, const int16_t* fresh_dev, int32_t count, int64_t stream_stride,
+                             float* bars_dev, int32_t* bars_i32_dev, fftl_beat* beat_dev, void* cuda_stream);
+int  fftl_stream_push(fftl_stream* s, const int16_t* fresh_host, int32_t count, int64_t stream_stride,
+                      float* bars_host, int32_t* bars_i32_host, fftl_beat* beat_host);
+int64_t fftl_stream_launch_count(const fftl_stream* s);
+
 /* Pinned host memory helpers. */
 void* fftl_host_alloc(uint64_t bytes);
 void  fftl_host_free(void* p);

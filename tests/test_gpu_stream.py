@@ -1,0 +1,136 @@
+"""GPU tests of the many-stream real-time front end (fftl_stream_*): the sliding window of
+GetAudioBuffer/MoveArray (reference wasapi_audio.cpp:390-484) + one WM_TIMER tick per push."""
+import ctypes as C
+
+import numpy as np
+import pytest
+
+from helpers import assert_bars_close, assert_int_heights
+
+pytestmark = pytest.mark.gpu
+
+
+def _ocfg(O, cfg):
+    oc = O.Config()
+    C.memmove(C.byref(oc), C.byref(cfg), C.sizeof(oc))
+    return oc
+
+
+def move_array_reference(dest, fresh):
+    """MoveArray as written in the reference (wasapi_audio.cpp:390-400), int16 input instead of float*65536:
+    the old samples are copied from k + addCount - 1, i.e. shifted by one less than addCount."""
+    n, add = dest.shape[0], fresh.shape[0]
+    out = dest.copy()
+    for k in range(n - add):
+        out[k] = out[k + add - 1]
+    out[n - add:] = fresh
+    return out
+
+
+def move_array_exact(dest, fresh):
+    n, add = dest.shape[0], fresh.shape[0]
+    if add >= n:
+        return fresh[add - n:].copy()
+    return np.concatenate([dest[add:], fresh])
+
+
+@pytest.mark.parametrize("mode", ["exact", "reference"])
+def test_streaming_ticks_match_oracle(oracle, lib, mode):
+    n, B, streams = 1024, 64, 7
+    cfg = lib.extended_config(n, 1024, B) if mode == "exact" else lib.reference_config(n, 1024, 100)
+    B = cfg.bars
+    oc = _ocfg(oracle, cfg)
+    rng = np.random.default_rng(11)
+    counts = [1024, 512, 480, 1, 777, 1024, 300] + [int(c) for c in rng.integers(200, 1025, 40)]
+    if mode == "exact":
+        counts[3] = 1500                         # more new samples than the window holds
+    total = sum(counts)
+    src = oracle.synth_pcm(streams, total)
+    win = np.zeros((streams, n), np.int16)
+    mover = move_array_exact if mode == "exact" else move_array_reference
+    got_w = np.zeros((streams, len(counts)), np.int32)
+    got_bass = np.zeros_like(got_w)
+    got_beat = []
+    pos = 0
+    with lib.StreamingSpectrum(cfg, streams, lib.MOVE_EXACT if mode == "exact" else lib.MOVE_REFERENCE) as ss:
+        for k, c in enumerate(counts):
+            fresh = src[:, pos:pos + c]
+            pos += c
+            got = ss.push(fresh)
+            ref_h = np.zeros((streams, B))
+            ref_i = np.zeros((streams, B), np.int32)
+            for s in range(streams):
+                win[s] = mover(win[s], fresh[s])
+                _, ref_h[s], ref_i[s] = oracle.frame(oc, win[s])
+            assert_bars_close(got["bars"], ref_h, "tick %d" % k)
+            assert_int_heights(got["bars_i32"], ref_i, ref_h, "tick %d" % k)
+            got_w[:, k] = got["beat"]["w"]
+            got_bass[:, k] = got["beat"]["bass"]
+            got_beat.append(got["beat"].copy())
+        assert ss.launch_count == 4 * len(counts)
+    # integer stages replayed by the oracle on the GPU's own (w, bass) series: bit exact
+    for s in range(streams):
+        rep = oracle.beat_replay(oc, got_w[s], got_bass[s])
+        for k in range(len(counts)):
+            b = got_beat[k][s]
+            assert (b["thr"], b["beat_value"], b["flag"]) == (rep["thr"][k], rep["beat_value"][k], rep["flag"][k]), (s, k)
+        agree = np.mean([got_beat[k][s]["peak_index"] == rep["peak_index"][k] for k in range(len(counts))])
+        assert agree >= 0.9
+        for k, c in enumerate(counts):
+            b = got_beat[k][s]
+            td = np.float32(min(c, 10 ** 9)) / np.float32(cfg.sample_rate)
+            assert b["movement_per_sec"] == np.float32(np.float32(n) * td) * np.float32(b["peak_index"])
+
+
+def test_streaming_equals_batched_stft_for_constant_hop(oracle, lib):
+    """With a constant count the stream is an STFT with hop = count over [zeros(n), samples]."""
+    n, hop, B, streams, ticks = 2048, 512, 100, 4, 60
+    cfg = lib.reference_config(n, hop, B)
+    src = oracle.synth_pcm(streams, hop * ticks)
+    padded = np.concatenate([np.zeros((streams, n), np.int16), src], axis=1)
+    with lib.BatchedSpectrum(cfg) as sp:
+        full = sp.run(padded)               # frame f+1 = window after push f
+    with lib.StreamingSpectrum(cfg, streams) as ss:
+        for k in range(ticks):
+            got = ss.push(src[:, k * hop:(k + 1) * hop])
+            ref = full["bars"][:, k + 1]
+            fmax = np.abs(ref).max(axis=-1, keepdims=True)
+            assert (np.abs(got["bars"] - ref) <= 2e-6 * fmax + 1e-12).all()   # different frame pairing: rounding only
+        ss.reset()
+        again = ss.push(src[:, :hop])
+        assert (np.abs(again["bars"] - full["bars"][:, 1]) <= 2e-6 * np.abs(full["bars"][:, 1]).max()).all()
+        assert (again["beat"]["thr"] == again["beat"]["w"] // 160).all()       # rings were zeroed
+
+
+def test_streaming_cuda_graph_replay(oracle, lib):
+    import torch
+    n, B, streams, count = 1024, 64, 1024, 256
+    cfg = lib.extended_config(n, count, B)
+    src = torch.from_numpy(oracle.synth_pcm(streams, count * 12)).cuda()
+    fresh = torch.empty((streams, count), dtype=torch.int16, device="cuda")
+    bars = torch.empty((streams, B), dtype=torch.float32, device="cuda")
+    beat = torch.empty((streams, 8), dtype=torch.int32, device="cuda")
+    ref_bars, ref_beat = [], []
+    with lib.StreamingSpectrum(cfg, streams) as ss:
+        for k in range(12):
+            fresh.copy_(src[:, k * count:(k + 1) * count])
+            ss.push_device(fresh, bars, None, beat)
+            torch.cuda.synchronize()
+            ref_bars.append(bars.clone()); ref_beat.append(beat.clone())
+    with lib.StreamingSpectrum(cfg, streams) as ss:
+        st = torch.cuda.Stream()
+        with torch.cuda.stream(st):
+            fresh.copy_(src[:, :count])
+            ss.push_device(fresh, bars, None, beat, stream=st)          # tick 0 outside the graph (warm-up)
+            st.synchronize()
+            assert torch.equal(bars, ref_bars[0])
+            g = torch.cuda.CUDAGraph()
+            fresh.copy_(src[:, count:2 * count])
+            with torch.cuda.graph(g, stream=st):
+                ss.push_device(fresh, bars, None, beat, stream=st)
+            for k in range(1, 12):                                      # capture did not execute: replay ticks 1..11
+                fresh.copy_(src[:, k * count:(k + 1) * count])
+                g.replay()
+                st.synchronize()
+                assert torch.equal(bars, ref_bars[k]), k
+                assert torch.equal(beat, ref_beat[k]), k

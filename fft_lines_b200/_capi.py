@@ -32,6 +32,13 @@ class FftlConfig(C.Structure):
         return c
 
 
+class FftlSettings(C.Structure):
+    """fftl_settings: the 11 numbers of the reference's Settings.txt (settingsFile.c:376)."""
+    _fields_ = [("bar_count", C.c_int32), ("zoom", C.c_float), ("color_sel", C.c_int32), ("dofft", C.c_int32),
+                ("background", C.c_int32), ("gradient", C.c_int32), ("ignore_serial", C.c_int32), ("circle", C.c_int32),
+                ("waveform", C.c_int32), ("stereo", C.c_int32), ("beat_detection", C.c_int32)]
+
+
 class FftlBeat(C.Structure):
     """fftl_beat (include/fftlines.h)."""
     _fields_ = [
@@ -48,7 +55,9 @@ EXPORTED_FUNCTIONS = {
         "fftl_build_sg", "fftl_stft_create", "fftl_stft_destroy", "fftl_stft_num_frames",
         "fftl_stft_run_device", "fftl_stft_run", "fftl_stft_launch_count", "fftl_stft_timing",
         "fftl_stream_create", "fftl_stream_destroy", "fftl_stream_reset", "fftl_stream_push_device",
-        "fftl_stream_push", "fftl_stream_launch_count", "fftl_host_alloc", "fftl_host_free", "fftl_synth_pcm_device", "fftl_measure_fp32_peak", "fftl_last_error",
+        "fftl_stream_push", "fftl_stream_launch_count", "fftl_settings_default", "fftl_settings_parse", "fftl_settings_format",
+        "fftl_settings_to_config", "fftl_color_index", "fftl_led_bytes_device", "fftl_marker_sweep_device",
+        "fftl_host_alloc", "fftl_host_free", "fftl_synth_pcm_device", "fftl_measure_fp32_peak", "fftl_last_error",
         "fftl_last_error_string", "fftl_clear_error", "fftl_version", "fftl_device_count",
         "fftl_set_n", "fftl_get_n", "fftl_compat_reset_beat", "fftl_compat_launch_count",
     ],
@@ -105,6 +114,16 @@ def lib():
     L.fftl_stream_push.argtypes = [vp, vp, C.c_int32, C.c_int64, vp, vp, vp]
     L.fftl_stream_launch_count.argtypes = [vp]
     L.fftl_stream_launch_count.restype = C.c_int64
+    L.fftl_settings_default.argtypes = [C.POINTER(FftlSettings)]
+    L.fftl_settings_default.restype = None
+    L.fftl_settings_parse.argtypes = [C.c_char_p, C.c_int64, C.POINTER(FftlSettings)]
+    L.fftl_settings_format.argtypes = [C.POINTER(FftlSettings), C.c_char_p, C.c_int64]
+    L.fftl_settings_to_config.argtypes = [C.POINTER(FftlSettings), C.c_int32, C.c_int32, C.c_float, cfgp]
+    L.fftl_settings_to_config.restype = None
+    L.fftl_color_index.argtypes = [C.c_int32, C.c_int32]
+    L.fftl_color_index.restype = C.c_uint32
+    L.fftl_led_bytes_device.argtypes = [vp, C.c_int64, C.c_int32, C.c_int32, vp, vp, vp]
+    L.fftl_marker_sweep_device.argtypes = [vp, C.c_int64, C.c_float, C.c_int32, C.c_int32, vp, vp, vp]
     L.fftl_host_alloc.argtypes = [C.c_uint64]
     L.fftl_host_alloc.restype = vp
     L.fftl_host_free.argtypes = [vp]

@@ -962,6 +962,90 @@ extern "C" int fftl_stream_push(fftl_stream* s, const int16_t* fresh, int32_t co
     return FFTL_OK;
 }
 
+// ------------------------------------------------------------------ callers / sinks either side of the path
+extern "C" void fftl_settings_default(fftl_settings* s)
+{
+    // settingsFile.h:10-22
+    s->bar_count = 500;
+    s->zoom = 0.0001f;
+    s->color_sel = 0;
+    s->dofft = 1;
+    s->background = 1;
+    s->gradient = 1;
+    s->ignore_serial = 1;
+    s->circle = 0;
+    s->waveform = 0;
+    s->stereo = 0;
+    s->beat_detection = 1;
+}
+
+extern "C" int fftl_settings_parse(const char* text, int64_t len, fftl_settings* out)
+{
+    if (!text || !out) return set_error(FFTL_ERR_ARG, "settings: NULL argument");
+    fftl_settings_default(out);
+    // readSettings leaves everything at its default for an empty or oversized file (settingsFile.c:178-181)
+    if (len <= 0 || len > 1000) return FFTL_OK;
+    std::vector<char> buf(text, text + len);
+    buf.push_back(0);
+    char* p = buf.data();
+    long bc = strtol(p, &p, 10);
+    out->bar_count = (bc < 100 || bc > 1000) ? 500 : (int32_t)bc;                 // :200-202
+    float z = strtof(p, &p);
+    out->zoom = (z < 0.00001f || z > 0.001f) ? 0.0001f : z;                         // :204-206
+    long long cs = strtoll(p, &p, 10);
+    out->color_sel = (cs < 0 || cs >= 6) ? 0 : (int32_t)cs;                        // :208-210
+    // the remaining eight are C `bool`s in the reference: any non-zero number reads as true (:213-243)
+    int32_t* flags[8] = {&out->dofft, &out->background, &out->gradient, &out->ignore_serial,
+                         &out->circle, &out->waveform, &out->stereo, &out->beat_detection};
+    for (int i = 0; i < 8; i++) *flags[i] = strtol(p, &p, 10) != 0 ? 1 : 0;
+    return FFTL_OK;
+}
+
+extern "C" int fftl_settings_format(const fftl_settings* s, char* buf, int64_t cap)
+{
+    if (!s || !buf || cap <= 0) return -1;
+    int n = snprintf(buf, (size_t)cap, "%d %0.6f %lld %d %d %d %d %d %d %d %d", s->bar_count, (double)s->zoom, (long long)s->color_sel,
+                     s->dofft, s->background, s->gradient, s->ignore_serial, s->circle, s->waveform, s->stereo, s->beat_detection); // :376
+    return (n < 0 || n >= cap) ? -1 : n;
+}
+
+extern "C" void fftl_settings_to_config(const fftl_settings* s, int32_t n, int32_t hop, float sample_rate, fftl_config* cfg)
+{
+    fftl_config_reference(cfg, n, hop, s->bar_count);
+    cfg->zoom = s->zoom;
+    cfg->circle = s->circle;
+    cfg->sample_rate = sample_rate;
+}
+
+extern "C" uint32_t fftl_color_index(int32_t i, int32_t count)
+{
+    // RANGE255 (drawBar2D.cpp:33): float division by (float - 1.0) is done in double, cast to float, then to unsigned
+    return (unsigned int)((float)(((float)i / ((float)count - 1.0)) * 254.0));
+}
+
+extern "C" int fftl_led_bytes_device(const int32_t* heights, int64_t frames, int32_t bars, int32_t led_bar, uint8_t* bytes,
+                                     uint8_t* valid, void* cuda_stream)
+{
+    if (!heights || !bytes || frames < 0 || bars < 1 || led_bar < 0 || led_bar >= bars) return set_error(FFTL_ERR_ARG, "bad LED arguments");
+    if (frames == 0) return FFTL_OK;
+    long long blocks = (frames + 255) / 256;
+    if (blocks > 4096) blocks = 4096;
+    led_bytes_kernel<<<(unsigned)blocks, 256, 0, (cudaStream_t)cuda_stream>>>(heights, frames, bars, led_bar, bytes, valid);
+    CUDA_TRY(cudaGetLastError());
+    return FFTL_OK;
+}
+
+extern "C" int fftl_marker_sweep_device(const fftl_beat* beat, int64_t frames, float time_delta, int32_t start_pos, int32_t start_dir,
+                                        int32_t* pos_out, int32_t* dir_out, void* cuda_stream)
+{
+    if (!beat || !pos_out || frames < 0) return set_error(FFTL_ERR_ARG, "bad marker arguments");
+    if (start_pos < 0 || start_pos > 2048 || start_dir < -1 || start_dir > 1) return set_error(FFTL_ERR_ARG, "marker start state out of range");
+    if (frames == 0) return FFTL_OK;
+    marker_sweep_kernel<<<1, 1024, 0, (cudaStream_t)cuda_stream>>>(beat, frames, time_delta, start_pos, start_dir, pos_out, dir_out);
+    CUDA_TRY(cudaGetLastError());
+    return FFTL_OK;
+}
+
 extern "C" void* fftl_host_alloc(uint64_t bytes)
 {
     void* p = nullptr;

@@ -597,6 +597,73 @@ __global__ void __launch_bounds__(256) synth_pcm_kernel(const SynthParams p, con
 }
 
 // --------------------------------------------------------------------------
+// Serial/LED sink (fft_lines.c:250-255): byte = (char)((float)height * 0.1f), only for height >= 0.
+__global__ void __launch_bounds__(256) led_bytes_kernel(const int* __restrict__ heights, long long frames, int bars, int led_bar,
+                                                        unsigned char* __restrict__ bytes, unsigned char* __restrict__ valid)
+{
+    for (long long f = (long long)blockIdx.x * blockDim.x + threadIdx.x; f < frames; f += (long long)gridDim.x * blockDim.x) {
+        const int h = heights[f * bars + led_bar];
+        const float v = __fmul_rn((float)h, 0.1f);
+        bytes[f] = (unsigned char)(trunc_i32(v, 1) & 0xff); // (char) of the truncated value keeps the low 8 bits
+        if (valid) valid[f] = h >= 0 ? 1 : 0;
+    }
+}
+
+// Beat-marker sweep (fft_lines.c:266-274).  The bouncing walk is a triangle wave of period 4096 in the total
+// number of steps, so the sequential loop becomes an inclusive prefix sum of the per-frame step counts.
+// One CTA; frames are scanned in chunks of 1024.
+__global__ void __launch_bounds__(1024) marker_sweep_kernel(const fftl_beat* __restrict__ beat, long long frames, float time_delta,
+                                                            int start_pos, int start_dir, int* __restrict__ pos_out,
+                                                            int* __restrict__ dir_out)
+{
+    __shared__ long long warp_tot[32];
+    __shared__ long long carry;
+    const int tid = threadIdx.x, lane = tid & 31, wid = tid >> 5;
+    if (tid == 0) carry = (start_dir < 0) ? (4096 - start_pos) : start_pos; // phase of the triangle wave
+    __syncthreads();
+    for (long long base = 0; base < frames; base += 1024) {
+        const long long f = base + tid;
+        long long k = 0;
+        if (f < frames) {
+            const float x = __fmul_rn(beat[f].movement_per_sec, time_delta); // (float)beatMovementPerSec * timeDelta
+            // for (int i = 0; i < x; i++): ceil(x) iterations for x > 0
+            if (x > 0.0f) k = (long long)ceilf(x);
+        }
+        long long incl = k;
+#pragma unroll
+        for (int o = 1; o < 32; o <<= 1) {
+            long long n = __shfl_up_sync(0xffffffffu, incl, o);
+            if (lane >= o) incl += n;
+        }
+        if (lane == 31) warp_tot[wid] = incl;
+        __syncthreads();
+        if (wid == 0) {
+            long long w = warp_tot[lane], wi = w;
+#pragma unroll
+            for (int o = 1; o < 32; o <<= 1) {
+                long long n = __shfl_up_sync(0xffffffffu, wi, o);
+                if (lane >= o) wi += n;
+            }
+            warp_tot[lane] = wi - w; // exclusive
+        }
+        __syncthreads();
+        const long long total = carry + warp_tot[wid] + incl; // steps made up to and including this frame (+ start phase)
+        if (f < frames) {
+            const int ph = (int)(total & 4095);
+            pos_out[f] = ph <= 2048 ? ph : 4096 - ph;
+            if (dir_out) {
+                // direction after the frame: unchanged if no step was ever made; +1 while rising, -1 while falling
+                const bool moved = (total - ((start_dir < 0) ? (4096 - start_pos) : start_pos)) > 0;
+                dir_out[f] = !moved ? start_dir : ((ph >= 1 && ph <= 2048) ? 1 : -1);
+            }
+        }
+        __syncthreads();
+        if (tid == 1023) carry = total;
+        __syncthreads();
+    }
+}
+
+// --------------------------------------------------------------------------
 // FP32 FMA throughput probe: the compute roofline's denominator is not in
 // MEASURED_PEAKS.json, so bench.py measures it on the box.
 __global__ void __launch_bounds__(256) fp32_peak_kernel(float* out, int iters, float a, float b)

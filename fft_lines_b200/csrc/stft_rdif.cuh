@@ -53,13 +53,22 @@ struct RdifParams {
 
 // Real 16-point DFT: x[0..15] real -> Y[0..8] (Y[0], Y[8] real).  66 flops.
 // yr/yi are indexed by k0; yi[0] and yi[8] are not written.
-__device__ __forceinline__ void real_dft16(const float* x, float* yr, float* yi)
+// WINDOWED: the inputs are x[q]*w[q]; the multiply is folded into the first butterfly stage
+// (one FMUL + two FFMA per pair instead of two FMUL + two FADD).
+template <bool WINDOWED>
+__device__ __forceinline__ void real_dft16(const float* x, const float* w, float* yr, float* yi)
 {
     float s[8], d[8];
 #pragma unroll
     for (int q = 0; q < 8; q++) {
-        s[q] = x[q] + x[q + 8];
-        d[q] = x[q] - x[q + 8];
+        if (WINDOWED) {
+            const float hi = x[q + 8] * w[q + 8];
+            s[q] = fmaf(x[q], w[q], hi);
+            d[q] = fmaf(x[q], w[q], -hi);
+        } else {
+            s[q] = x[q] + x[q + 8];
+            d[q] = x[q] - x[q + 8];
+        }
     }
     // even outputs: real 8-point DFT of s
     float a0 = s[0] + s[4], a1 = s[1] + s[5], a2 = s[2] + s[6], a3 = s[3] + s[7];
@@ -283,10 +292,8 @@ __global__ void __launch_bounds__(RdifShape<N, F>::THREADS, MINB) stft_bars_rdif
 #pragma unroll
             for (int h = 0; h < 2; h++) {
                 const int f = 2 * pr + h;
-                float x[16], yr[9], yi[9];
-#pragma unroll
-                for (int q = 0; q < 16; q++) x[q] = WINDOWED ? xr[q + HOPQ * f] * win[q] : xr[q + HOPQ * f];
-                real_dft16(x, yr, yi);
+                float yr[9], yi[9];
+                real_dft16<WINDOWED>(xr + HOPQ * f, win, yr, yi);
                 y0[h] = yr[0];
                 y8[h] = yr[8];
                 // slots 2*k0 + h (k0 = 1..7): frame h of the pair, residue k0

@@ -164,6 +164,36 @@ int  fftl_stream_push(fftl_stream* s, const int16_t* fresh_host, int32_t count, 
                       float* bars_host, int32_t* bars_i32_host, fftl_beat* beat_host);
 int64_t fftl_stream_launch_count(const fftl_stream* s);
 
+/* ---- callers and sinks either side of the path -----
+ * Settings line: the 11 space-separated numbers of Settings.txt, same order, same clamps and defaults as
+ * readSettings/writeSettings (settingsFile.c:172-247, :368-378, limits settingsFile.h:4-25).               */
+typedef struct fftl_settings {
+    int32_t bar_count;      /* 100..1000, default 500 */
+    float   zoom;           /* 1e-5..1e-3, default 1e-4 */
+    int32_t color_sel;      /* 0..5, default 0 */
+    int32_t dofft, background, gradient, ignore_serial, circle, waveform, stereo, beat_detection; /* 0/1 */
+} fftl_settings;
+void fftl_settings_default(fftl_settings* s);
+int  fftl_settings_parse(const char* text, int64_t len, fftl_settings* out);
+/* writes "%d %0.6f %lld %d %d %d %d %d %d %d %d"; returns the length or -1 if cap is too small */
+int  fftl_settings_format(const fftl_settings* s, char* buf, int64_t cap);
+/* reference-mode config (n, hop, sample_rate are not in Settings.txt) from a settings record */
+void fftl_settings_to_config(const fftl_settings* s, int32_t n, int32_t hop, float sample_rate, fftl_config* cfg);
+
+/* RANGE255(i, count): brush / colour-map index of bar i (drawBar2D.cpp:33).                                 */
+uint32_t fftl_color_index(int32_t i, int32_t count);
+
+/* Serial/LED sink (fft_lines.c:250-255): one byte per frame, (char)(height[led_bar] * 0.1f), sent only when
+ * the height is >= 0.  heights: int32 [frames][bars]; out bytes [frames]; valid [frames] (may be NULL).     */
+int fftl_led_bytes_device(const int32_t* heights_dev, int64_t frames, int32_t bars, int32_t led_bar,
+                          uint8_t* bytes_dev, uint8_t* valid_dev, void* cuda_stream);
+
+/* Beat-marker sweep (fft_lines.c:266-274): per frame the marker makes ceil(beatMovementPerSec*timeDelta)
+ * unit steps, bouncing between 0 and 2048.  beat: [frames] records of ONE channel; pos_out/dir_out [frames]
+ * hold beatposition / direction after each frame.  start_pos in 0..2048, start_dir -1, 0 or 1.              */
+int fftl_marker_sweep_device(const fftl_beat* beat_dev, int64_t frames, float time_delta, int32_t start_pos,
+                             int32_t start_dir, int32_t* pos_out_dev, int32_t* dir_out_dev, void* cuda_stream);
+
 /* Pinned host memory helpers. */
 void* fftl_host_alloc(uint64_t bytes);
 void  fftl_host_free(void* p);

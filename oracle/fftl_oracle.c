@@ -534,3 +534,63 @@ void orc_synth_pcm(int16_t* pcm, int32_t channels, int64_t samples, int64_t cs, 
         }
     }
 }
+
+/* ------------------------------------------------- callers / sinks
+ * Restated from the reference; test infrastructure like the rest of this file. */
+
+/* readSettings (settingsFile.c:172-247): 11 numbers, each clamped to its default when out of range.
+ * v[0]=barCount v[1]=zoom (as float bits via *zoom) v[2]=colorSel v[3..10] = the eight bools. */
+void orc_settings_parse(const char* text, long len, int32_t* v, float* zoom)
+{
+    v[0] = 500; *zoom = 0.0001f; v[2] = 0;           /* settingsFile.h:10,13,14 */
+    v[3] = 1; v[4] = 1; v[5] = 1; v[6] = 1; v[7] = 0; v[8] = 0; v[9] = 0; v[10] = 1; /* settingsFile.h:15-22 */
+    if (len > 1000 || len == 0) return;              /* :178-181 */
+    char* buffer = (char*)malloc((size_t)len + 1);
+    memcpy(buffer, text, (size_t)len);
+    buffer[len] = 0;
+    char* next;
+    long barCount = strtol(buffer, &next, 10);       /* :200 */
+    if (barCount < 100 || barCount > 1000) barCount = 500;
+    v[0] = (int32_t)barCount;
+    float z = strtof(next, &next);                   /* :204 */
+    if (z < 0.00001f || z > 0.001f) z = 0.0001f;
+    *zoom = z;
+    long long colorSel = strtoll(next, &next, 10);   /* :208 */
+    if (colorSel < 0 || colorSel >= 6) colorSel = 0;
+    v[2] = (int32_t)colorSel;
+    for (int i = 3; i <= 10; i++) {                  /* :213-243: `bool x = strtol(...)` */
+        _Bool b = strtol(next, &next, 10);
+        v[i] = b;
+    }
+    free(buffer);
+}
+
+/* RANGE255 (drawBar2D.cpp:33) */
+uint32_t orc_range255(int number, int maxValueOfNumber)
+{
+    return (unsigned int)((float)(((float)number / ((float)maxValueOfNumber - 1.0)) * 254.0));
+}
+
+/* fft_lines.c:250-255: line[0] = (char)((float)barLeft[led_bar].height * 0.1f), sent when height >= 0 */
+void orc_led_byte(int32_t height, uint8_t* byte, uint8_t* valid)
+{
+    float v = (float)height * 0.1f;
+    *byte = (uint8_t)(orc_trunc_i32((double)v, 1) & 0xff);
+    *valid = height >= 0;
+}
+
+/* fft_lines.c:266-274, verbatim loop, over a series of beatMovementPerSec values */
+void orc_marker_sweep(const float* movement, int64_t frames, float timeDelta, int32_t beatposition, int32_t direction,
+                      int32_t* pos_out, int32_t* dir_out)
+{
+    for (int64_t f = 0; f < frames; f++) {
+        float beatMovementPerSec = movement[f];
+        for (int i = 0; i < (float)beatMovementPerSec * timeDelta; i++) {
+            if (beatposition >= 2048) direction = -1;
+            if (beatposition <= 0) direction = 1;
+            beatposition += direction;
+        }
+        pos_out[f] = beatposition;
+        dir_out[f] = direction;
+    }
+}

@@ -83,6 +83,14 @@ void orc_beat_replay(const fftl_config* cfg, const int32_t* w, const int32_t* ba
 void orc_synth_pcm(int16_t* pcm, int32_t channels, int64_t samples, int64_t channel_stride,
                    int64_t first_sample, float sample_rate, uint32_t seed);
 
+/* Callers / sinks either side of the path, restated from settingsFile.c:172-247,
+ * drawBar2D.cpp:33, fft_lines.c:250-255 and fft_lines.c:266-274. */
+void orc_settings_parse(const char* text, long len, int32_t* v /*[11]*/, float* zoom);
+uint32_t orc_range255(int number, int maxValueOfNumber);
+void orc_led_byte(int32_t height, uint8_t* byte, uint8_t* valid);
+void orc_marker_sweep(const float* movement, int64_t frames, float timeDelta, int32_t beatposition, int32_t direction,
+                      int32_t* pos_out, int32_t* dir_out);
+
 #ifdef __cplusplus
 }
 #endif

@@ -129,6 +129,11 @@ def lib():
                                C.c_int64, C.c_int64, f64p, f32p, i32p, C.c_void_p]
         L.orc_beat_replay.argtypes = [C.POINTER(Config), i32p, i32p, C.c_int64, C.c_int64, C.c_void_p, i32p]
         L.orc_synth_pcm.argtypes = [i16p, C.c_int32, C.c_int64, C.c_int64, C.c_int64, C.c_float, C.c_uint32]
+        L.orc_settings_parse.argtypes = [C.c_char_p, C.c_long, i32p, f32p]
+        L.orc_range255.restype = C.c_uint32
+        L.orc_range255.argtypes = [C.c_int, C.c_int]
+        L.orc_led_byte.argtypes = [C.c_int32, C.POINTER(C.c_uint8), C.POINTER(C.c_uint8)]
+        L.orc_marker_sweep.argtypes = [f32p, C.c_int64, C.c_float, C.c_int32, C.c_int32, i32p, i32p]
         L.port_max_threads.restype = C.c_int
         L.port_run.restype = C.c_double
         L.port_run.argtypes = [C.POINTER(Config), i16p, C.c_int32, C.c_int64, C.c_int64, C.c_int64,
@@ -322,3 +327,35 @@ def ref_run(pcm, hop, bars, zoom=1e-4, circle=0, beat=True, sample_rate=48000.0,
     finally:
         R.ref_close()
     return sec, heights, fo
+
+
+def settings_parse(text):
+    """readSettings restated: returns ([11 ints, zoom slot unused], zoom)."""
+    raw = text.encode() if isinstance(text, str) else bytes(text)
+    v = np.zeros(11, np.int32)
+    z = C.c_float()
+    lib().orc_settings_parse(raw, len(raw), _p(v, C.c_int32), C.byref(z))
+    return v, z.value
+
+
+def range255(i, count):
+    return int(lib().orc_range255(i, count))
+
+
+def led_bytes(heights):
+    heights = np.ascontiguousarray(heights, np.int32)
+    b = np.zeros(heights.shape, np.uint8)
+    v = np.zeros(heights.shape, np.uint8)
+    bb, vv = C.c_uint8(), C.c_uint8()
+    for i, h in enumerate(heights.ravel()):
+        lib().orc_led_byte(int(h), C.byref(bb), C.byref(vv))
+        b.ravel()[i], v.ravel()[i] = bb.value, vv.value
+    return b, v
+
+
+def marker_sweep(movement, time_delta, pos=0, direction=0):
+    movement = np.ascontiguousarray(movement, np.float32)
+    p = np.zeros(movement.shape[0], np.int32)
+    d = np.zeros(movement.shape[0], np.int32)
+    lib().orc_marker_sweep(_p(movement, C.c_float), movement.shape[0], time_delta, pos, direction, _p(p, C.c_int32), _p(d, C.c_int32))
+    return p, d

@@ -40,29 +40,31 @@ with F.BatchedSpectrum(F.reference_config(2048, 512, 100)) as sp:
 out.append({"config": "c1: 10 s stereo 48 kHz, 2048-pt, hop 512 (assumed), 100 bars, reference mode", "frames": frames,
             "ms": ms, "bars_kernel_ms": bms, "frames_per_s": frames / ms * 1e3, "kernel": "stft_bars_kernel<2048> (generic)"})
 
-# ---- c3: 1024 concurrent mono streams, one 1024-sample frame each per batch, 64 bars -> latency per batch
-pcm = torch.empty((1024, 1024), dtype=torch.int16, device=dev)
-F.synth_pcm_device(pcm)
-cfg3 = F.extended_config(1024, 1024, 64, sg_half=3, sg_degree=2)
-with F.BatchedSpectrum(cfg3) as sp:
-    bars, _, beat = sp.alloc_device_outputs(1024, 1, dev)
+# ---- c3: 1024 concurrent mono streams, 1024-pt window, 64 bars: one tick (512 new samples per stream) per batch
+# through the streaming front end (device-resident sliding windows + beat state)
+STREAMS, COUNT = 1024, 512
+src = torch.empty((STREAMS, COUNT * 64), dtype=torch.int16, device=dev)
+F.synth_pcm_device(src)
+cfg3 = F.extended_config(1024, COUNT, 64, sg_half=3, sg_degree=2)
+with F.StreamingSpectrum(cfg3, STREAMS) as ss:
+    fresh = src[:, :COUNT].contiguous()
+    bars = torch.empty((STREAMS, 64), dtype=torch.float32, device=dev)
+    beat = torch.empty((STREAMS, 8), dtype=torch.int32, device=dev)
     st = torch.cuda.Stream()
     with torch.cuda.stream(st):
         for _ in range(5):
-            sp.run_device(pcm, bars, None, beat, stream=st)
+            ss.push_device(fresh, bars, None, beat, stream=st)
         st.synchronize()
-        # (a) plain launches, synchronised per batch (what a real-time caller sees from Python)
         lat = []
         for _ in range(2000):
             t0 = time.perf_counter()
-            sp.run_device(pcm, bars, None, beat, stream=st)
+            ss.push_device(fresh, bars, None, beat, stream=st)
             st.synchronize()
             lat.append((time.perf_counter() - t0) * 1e6)
         lat_plain = np.array(lat[200:])
-        # (b) CUDA graph replay
         g = torch.cuda.CUDAGraph()
         with torch.cuda.graph(g, stream=st):
-            sp.run_device(pcm, bars, None, beat, stream=st)
+            ss.push_device(fresh, bars, None, beat, stream=st)
         lat = []
         for _ in range(2000):
             t0 = time.perf_counter()
@@ -70,7 +72,6 @@ with F.BatchedSpectrum(cfg3) as sp:
             st.synchronize()
             lat.append((time.perf_counter() - t0) * 1e6)
         lat_graph = np.array(lat[200:])
-        # (c) device time per batch: 200 back-to-back replays between two events
         e0, e1 = torch.cuda.Event(enable_timing=True), torch.cuda.Event(enable_timing=True)
         e0.record(st)
         for _ in range(200):
@@ -78,26 +79,25 @@ with F.BatchedSpectrum(cfg3) as sp:
         e1.record(st)
         st.synchronize()
         dev_us = e0.elapsed_time(e1) * 1e3 / 200
-    # (d) through the C-ABI host call with pinned buffers (H2D 2 MB, D2H 0.3 MB per batch)
-    h_pcm = F.PinnedArray((1024, 1024), np.int16)
-    h_pcm.array[:] = pcm.cpu().numpy()
-    h_bars = F.PinnedArray((1024, 1, 64), np.float32)
-    h_beat = F.PinnedArray((1024, 1), F.BEAT_DTYPE)
-    o = {"bars": h_bars.array, "beat": h_beat.array}
+    h_fresh = F.PinnedArray((STREAMS, COUNT), np.int16)
+    h_fresh.array[:] = fresh.cpu().numpy()
+    o = {"bars": F.PinnedArray((STREAMS, 64), np.float32).array, "beat": F.PinnedArray((STREAMS,), F.BEAT_DTYPE).array}
     for _ in range(20):
-        sp.run(h_pcm.array, want_i32=False, out=o)
+        ss.push(h_fresh.array, want_i32=False, out=o)
     lat = []
     for _ in range(1000):
         t0 = time.perf_counter()
-        sp.run(h_pcm.array, want_i32=False, out=o)
+        ss.push(h_fresh.array, want_i32=False, out=o)
         lat.append((time.perf_counter() - t0) * 1e6)
     lat_host = np.array(lat[100:])
 pct = lambda a: {"p50_us": float(np.percentile(a, 50)), "p99_us": float(np.percentile(a, 99))}
-out.append({"config": "c3: 1024 concurrent mono streams, 1024-pt Hann, 64 log bars + SG + beat, one frame per stream per batch",
-            "frames_per_batch": 1024, "device_us_per_batch_graph_back_to_back": dev_us,
+out.append({"config": "c3: 1024 concurrent mono streams, 1024-pt Hann, 64 log bars + SG + beat, one tick (512 new samples) per stream per batch",
+            "api": "fftl_stream_push[_device] (sliding windows and beat state resident on the GPU)",
+            "frames_per_batch": STREAMS, "device_us_per_batch_graph_back_to_back": dev_us,
             "launch_sync_python": pct(lat_plain), "cuda_graph_replay_sync_python": pct(lat_graph),
-            "c_abi_host_buffers_pinned": pct(lat_host), "frames_per_s_device": 1024 / dev_us * 1e6,
-            "note": "latency bound: 1024 frames are ~1 us of work at the roofline; kernels: stft_bars_kernel<1024> + beat_post_kernel"})
+            "c_abi_host_buffers_pinned": pct(lat_host), "frames_per_s_device": STREAMS / dev_us * 1e6,
+            "h2d_bytes_per_batch": STREAMS * COUNT * 2, "d2h_bytes_per_batch": STREAMS * 64 * 4 + STREAMS * 32,
+            "note": "latency bound: 1024 frames are ~1 us of work at the roofline; 4 launches per tick: stream_slide, stft_bars_kernel<1024>, stream_beat, stream_tick"})
 
 # ---- c4: 16384-pt window, 512 bars, stereo (1 min), hop 512 and 4096
 pcm = torch.empty((2, 48000 * 60), dtype=torch.int16, device=dev)

@@ -14,6 +14,7 @@
 
 #include "kernels.cuh"
 #include "stft_rdif.cuh"
+#include "stft_rdif3.cuh"
 #include "stream.cuh"
 #include "../../include/fft_calculate.h"
 #include "../../include/beatDetector.h"
@@ -479,6 +480,34 @@ static cudaError_t launch_rdif(const fftl_stft* h, RdifParams p, int channels, c
     return cudaGetLastError();
 }
 
+template <int HOPQ, bool WIN, int SGW>
+static cudaError_t launch_rdif3(const fftl_stft* h, RdifParams p, int channels, cudaStream_t st)
+{
+    using Sh = Rdif3Shape;
+    size_t smem = Sh::smem_bytes(p.bars_n, p.nseg, p.sg_half);
+    if ((smem + 1024) * 3 > 228 * 1024) return cudaErrorNotSupported; // three CTAs per SM is the design point
+    p.tiles_per_channel = (p.frame_end - p.frame0 + Sh::F - 1) / Sh::F;
+    p.total_tiles = p.tiles_per_channel * channels;
+    if (p.total_tiles <= 0) return cudaSuccess;
+    auto kern = stft_bars_rdif3_kernel<HOPQ, WIN, SGW>;
+    cudaError_t e = cudaFuncSetAttribute(kern, cudaFuncAttributeMaxDynamicSharedMemorySize, (int)smem);
+    if (e != cudaSuccess) return e;
+    long long grid = 3ll * h->num_sms;
+    if (grid > p.total_tiles) grid = p.total_tiles;
+    kern<<<(unsigned)grid, 256, smem, st>>>(p);
+    return cudaGetLastError();
+}
+
+template <int HOPQ, bool WIN>
+static cudaError_t launch_rdif3_sg(const fftl_stft* h, const RdifParams& p, int channels, cudaStream_t st)
+{
+    switch (p.sg_half) {
+    case 0: return launch_rdif3<HOPQ, WIN, 0>(h, p, channels, st);
+    case 3: return launch_rdif3<HOPQ, WIN, 3>(h, p, channels, st);
+    default: return launch_rdif3<HOPQ, WIN, -1>(h, p, channels, st);
+    }
+}
+
 template <int HOPQ, bool WIN>
 static cudaError_t launch_rdif_sg(const fftl_stft* h, const RdifParams& p, int channels, cudaStream_t st)
 {
@@ -534,6 +563,16 @@ static cudaError_t try_rdif(const fftl_stft* h, const StftParams& q, int channel
     p.zoom = q.zoom;
     p.circle_add = q.circle_add;
     const bool win = q.window != nullptr;
+    static const bool use3 = getenv("FFTL_RDIF3") != nullptr; // developer A/B switch
+    if (use3) {
+        cudaError_t e3;
+        switch (hopq) {
+        case 1: e3 = win ? launch_rdif3_sg<1, true>(h, p, channels, st) : launch_rdif3_sg<1, false>(h, p, channels, st); break;
+        case 2: e3 = win ? launch_rdif3_sg<2, true>(h, p, channels, st) : launch_rdif3_sg<2, false>(h, p, channels, st); break;
+        default: e3 = win ? launch_rdif3_sg<4, true>(h, p, channels, st) : launch_rdif3_sg<4, false>(h, p, channels, st); break;
+        }
+        if (e3 != cudaErrorNotSupported) return e3;
+    }
     switch (hopq) {
     case 1: return win ? launch_rdif_sg<1, true>(h, p, channels, st) : launch_rdif_sg<1, false>(h, p, channels, st);
     case 2: return win ? launch_rdif_sg<2, true>(h, p, channels, st) : launch_rdif_sg<2, false>(h, p, channels, st);

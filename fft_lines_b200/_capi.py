@@ -55,7 +55,8 @@ EXPORTED_FUNCTIONS = {
         "fftl_build_sg", "fftl_stft_create", "fftl_stft_destroy", "fftl_stft_num_frames",
         "fftl_stft_run_device", "fftl_stft_run", "fftl_stft_launch_count", "fftl_stft_timing",
         "fftl_stream_create", "fftl_stream_destroy", "fftl_stream_reset", "fftl_stream_push_device",
-        "fftl_stream_push", "fftl_stream_launch_count", "fftl_settings_default", "fftl_settings_parse", "fftl_settings_format",
+        "fftl_stream_push", "fftl_stream_launch_count", "fftl_stream_set_history", "fftl_stream_history_device",
+        "fftl_stream_waveform_device", "fftl_settings_default", "fftl_settings_parse", "fftl_settings_format",
         "fftl_settings_to_config", "fftl_color_index", "fftl_led_bytes_device", "fftl_marker_sweep_device",
         "fftl_host_alloc", "fftl_host_free", "fftl_synth_pcm_device", "fftl_measure_fp32_peak", "fftl_last_error",
         "fftl_last_error_string", "fftl_clear_error", "fftl_version", "fftl_device_count",
@@ -112,6 +113,9 @@ def lib():
     L.fftl_stream_reset.argtypes = [vp]
     L.fftl_stream_push_device.argtypes = [vp, vp, C.c_int32, C.c_int64, vp, vp, vp, vp]
     L.fftl_stream_push.argtypes = [vp, vp, C.c_int32, C.c_int64, vp, vp, vp]
+    L.fftl_stream_set_history.argtypes = [vp, C.c_int32]
+    L.fftl_stream_history_device.argtypes = [vp, vp, vp]
+    L.fftl_stream_waveform_device.argtypes = [vp, C.c_int32, C.c_float, C.c_float, vp, vp]
     L.fftl_stream_launch_count.argtypes = [vp]
     L.fftl_stream_launch_count.restype = C.c_int64
     L.fftl_settings_default.argtypes = [C.POINTER(FftlSettings)]

@@ -851,6 +851,8 @@ struct fftl_stream {
     float* d_bars;
     int32_t* d_bars_i32;
     fftl_beat* d_beat;
+    float* d_hist;          // [streams][hist_depth][bars] or NULL
+    int hist_depth;
     int64_t launches;
 };
 
@@ -870,6 +872,7 @@ extern "C" void fftl_stream_destroy(fftl_stream* s)
     cudaFree(s->d_bars);
     cudaFree(s->d_bars_i32);
     cudaFree(s->d_beat);
+    cudaFree(s->d_hist);
     cudaGetLastError();
     fftl_stft_destroy(s->core);
     free(s);
@@ -885,6 +888,56 @@ extern "C" int fftl_stream_reset(fftl_stream* s)
     CUDA_TRY(cudaMemset(s->d_w_sum, 0, sizeof(int) * S));
     CUDA_TRY(cudaMemset(s->d_tempo_ring, 0, sizeof(int) * S * FFTL_TEMPO_RING));
     CUDA_TRY(cudaMemset(s->d_state, 0, sizeof(StreamState)));
+    if (s->d_hist) CUDA_TRY(cudaMemset(s->d_hist, 0, sizeof(float) * S * s->hist_depth * s->core->cfg.bars));
+    return FFTL_OK;
+}
+
+extern "C" int fftl_stream_set_history(fftl_stream* s, int32_t depth)
+{
+    if (!s) return set_error(FFTL_ERR_ARG, "stream handle is NULL");
+    if (depth < 0 || depth > 4096) return set_error(FFTL_ERR_ARG, "history depth %d out of 0..4096", depth);
+    CUDA_TRY(cudaSetDevice(s->core->device));
+    CUDA_TRY(cudaDeviceSynchronize());
+    cudaFree(s->d_hist);
+    s->d_hist = nullptr;
+    s->hist_depth = 0;
+    if (depth > 0) {
+        size_t bytes = sizeof(float) * (size_t)s->streams * depth * s->core->cfg.bars;
+        cudaError_t e = cudaMalloc(&s->d_hist, bytes);
+        if (e != cudaSuccess) return set_error(FFTL_ERR_NOMEM, "history allocation failed: %s", cudaGetErrorString(e));
+        CUDA_TRY(cudaMemset(s->d_hist, 0, bytes));
+        s->hist_depth = depth;
+    }
+    return FFTL_OK;
+}
+
+extern "C" int fftl_stream_history_device(fftl_stream* s, float* out, void* cuda_stream)
+{
+    if (!s || !out) return set_error(FFTL_ERR_ARG, "NULL argument");
+    if (!s->d_hist) return set_error(FFTL_ERR_STATE, "history is off: call fftl_stream_set_history first");
+    CUDA_TRY(cudaSetDevice(s->core->device));
+    long long total = (long long)s->streams * s->hist_depth * s->core->cfg.bars;
+    long long blocks = (total + 255) / 256;
+    if (blocks > 8192) blocks = 8192;
+    stream_history_read_kernel<<<(unsigned)blocks, 256, 0, (cudaStream_t)cuda_stream>>>(s->d_hist, out, s->d_state, s->streams, s->hist_depth,
+                                                                                       s->core->cfg.bars);
+    CUDA_TRY(cudaGetLastError());
+    s->launches++;
+    return FFTL_OK;
+}
+
+extern "C" int fftl_stream_waveform_device(fftl_stream* s, int32_t points, float scale, float offset, int32_t* heights, void* cuda_stream)
+{
+    if (!s || !heights) return set_error(FFTL_ERR_ARG, "NULL argument");
+    if (points < 1 || points > s->core->cfg.n) return set_error(FFTL_ERR_ARG, "points=%d outside 1..n", points);
+    CUDA_TRY(cudaSetDevice(s->core->device));
+    long long total = (long long)s->streams * points;
+    long long blocks = (total + 255) / 256;
+    if (blocks > 8192) blocks = 8192;
+    stream_waveform_kernel<<<(unsigned)blocks, 256, 0, (cudaStream_t)cuda_stream>>>(s->d_window, s->core->cfg.n, points, scale, offset, heights,
+                                                                                   s->streams);
+    CUDA_TRY(cudaGetLastError());
+    s->launches++;
     return FFTL_OK;
 }
 
@@ -968,6 +1021,14 @@ extern "C" int fftl_stream_push_device(fftl_stream* s, const int16_t* fresh, int
     bp.strict = c.strict_int;
     stream_beat_kernel<<<(s->streams + 31) / 32, 256, 0, st>>>(bp);
     CUDA_TRY(cudaGetLastError());
+    if (s->d_hist) {
+        long long total = (long long)s->streams * c.bars;
+        long long blocks = (total + 255) / 256;
+        if (blocks > 4096) blocks = 4096;
+        stream_history_push_kernel<<<(unsigned)blocks, 256, 0, st>>>(s->d_hist, bars, s->d_state, s->streams, s->hist_depth, c.bars);
+        CUDA_TRY(cudaGetLastError());
+        s->launches++;
+    }
     stream_tick_kernel<<<1, 1, 0, st>>>(s->d_state);
     CUDA_TRY(cudaGetLastError());
     s->launches += 4;

@@ -196,6 +196,48 @@ __global__ void __launch_bounds__(256) stream_beat_kernel(const StreamBeatParams
     }
 }
 
+// history ring: hist[s][tick % depth][b] = bars[s][b]
+__global__ void __launch_bounds__(256) stream_history_push_kernel(float* __restrict__ hist, const float* __restrict__ bars,
+                                                                  const StreamState* state, int streams, int depth, int nbars)
+{
+    const int slot = (int)(state->tick % depth);
+    const long long total = (long long)streams * nbars;
+    for (long long i = (long long)blockIdx.x * blockDim.x + threadIdx.x; i < total; i += (long long)gridDim.x * blockDim.x) {
+        const long long s = i / nbars;
+        const int b = (int)(i - s * nbars);
+        hist[(s * depth + slot) * nbars + b] = bars[i];
+    }
+}
+
+// out[s][k][b], k = 0 oldest ... depth-1 newest; `tick` pushes have been made so far
+__global__ void __launch_bounds__(256) stream_history_read_kernel(const float* __restrict__ hist, float* __restrict__ out,
+                                                                  const StreamState* state, int streams, int depth, int nbars)
+{
+    const long long tick = state->tick;
+    const long long total = (long long)streams * depth * nbars;
+    for (long long i = (long long)blockIdx.x * blockDim.x + threadIdx.x; i < total; i += (long long)gridDim.x * blockDim.x) {
+        const int b = (int)(i % nbars);
+        const long long sk = i / nbars;
+        const int k = (int)(sk % depth);
+        const long long s = sk / depth;
+        const long long age = depth - 1 - k;         // 0 = newest frame
+        const long long fr = tick - 1 - age;         // push index of that frame
+        out[i] = fr >= 0 ? hist[(s * depth + (fr % depth)) * nbars + b] : 0.0f;
+    }
+}
+
+// fft_lines.c:239-247: waveBar[i].height = audioBufferLeft[i] * 0.02f + offset  (float -> int assignment truncates)
+__global__ void __launch_bounds__(256) stream_waveform_kernel(const int16_t* __restrict__ window, int n, int points, float scale,
+                                                              float offset, int* __restrict__ heights, int streams)
+{
+    const long long total = (long long)streams * points;
+    for (long long i = (long long)blockIdx.x * blockDim.x + threadIdx.x; i < total; i += (long long)gridDim.x * blockDim.x) {
+        const long long s = i / points;
+        const int k = (int)(i - s * points);
+        heights[i] = trunc_i32(__fadd_rn(__fmul_rn((float)window[s * n + k], scale), offset), 1);
+    }
+}
+
 // advances the tick once per push, after every block of stream_beat_kernel has read it
 __global__ void stream_tick_kernel(StreamState* st) { st->tick++; }
 

@@ -71,3 +71,23 @@ class StreamingSpectrum:
             self._h, fresh.data_ptr(), fresh.shape[1], fresh.stride(0), bars.data_ptr(),
             bars_i32.data_ptr() if bars_i32 is not None else None, beat.data_ptr() if beat is not None else None,
             st.cuda_stream))
+
+    def set_history(self, depth):
+        """Keep the last ``depth`` bar frames of every stream on the device (the reference's 3D-mode trail)."""
+        _capi.check(_capi.lib().fftl_stream_set_history(self._h, depth))
+        self._depth = depth
+
+    def history_device(self, device="cuda"):
+        """torch float32 [streams, depth, bars], oldest frame first."""
+        import torch
+        out = torch.empty((self.streams, self._depth, self.cfg.bars), dtype=torch.float32, device=device)
+        _capi.check(_capi.lib().fftl_stream_history_device(self._h, out.data_ptr(), torch.cuda.current_stream(out.device).cuda_stream))
+        return out
+
+    def waveform_device(self, points=2048, scale=0.02, offset=0.0, device="cuda"):
+        """Waveform view of the current windows (fft_lines.c:239-247): int32 [streams, points]."""
+        import torch
+        out = torch.empty((self.streams, points), dtype=torch.int32, device=device)
+        _capi.check(_capi.lib().fftl_stream_waveform_device(self._h, points, scale, offset, out.data_ptr(),
+                                                            torch.cuda.current_stream(out.device).cuda_stream))
+        return out

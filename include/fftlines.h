@@ -163,6 +163,16 @@ int  fftl_stream_push_device(fftl_stream* s, const int16_t* fresh_dev, int32_t c
 int  fftl_stream_push(fftl_stream* s, const int16_t* fresh_host, int32_t count, int64_t stream_stride,
                       float* bars_host, int32_t* bars_i32_host, fftl_beat* beat_host);
 int64_t fftl_stream_launch_count(const fftl_stream* s);
+/* Render-side history (the reference's "3D mode" keeps the last ~96 bar frames on screen by feeding the
+ * bitmap back, drawBar2D.cpp:405-426,670-680).  depth > 0 keeps the last `depth` float bar frames of every
+ * stream on the device; fftl_stream_history_device copies them out oldest first as [streams][depth][bars]
+ * (frames before the first push read as 0).                                                              */
+int  fftl_stream_set_history(fftl_stream* s, int32_t depth);
+int  fftl_stream_history_device(fftl_stream* s, float* out_dev, void* cuda_stream);
+/* Waveform view (fft_lines.c:239-247): height[i] = (int)(window[i] * scale + offset) for the first `points`
+ * samples of every stream's current window (reference: 2048 points, scale 0.02, offset from the client rect). */
+int  fftl_stream_waveform_device(fftl_stream* s, int32_t points, float scale, float offset, int32_t* heights_dev,
+                                 void* cuda_stream);
 
 /* ---- callers and sinks either side of the path -----
  * Settings line: the 11 space-separated numbers of Settings.txt, same order, same clamps and defaults as

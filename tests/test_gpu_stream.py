@@ -134,3 +134,25 @@ def test_streaming_cuda_graph_replay(oracle, lib):
                 st.synchronize()
                 assert torch.equal(bars, ref_bars[k]), k
                 assert torch.equal(beat, ref_beat[k]), k
+
+
+def test_history_ring_and_waveform(oracle, lib):
+    import torch
+    n, B, streams, hop, depth = 2048, 100, 5, 512, 6
+    cfg = lib.reference_config(n, hop, B)
+    src = oracle.synth_pcm(streams, hop * 10)
+    frames = []
+    with lib.StreamingSpectrum(cfg, streams) as ss:
+        ss.set_history(depth)
+        for k in range(10):
+            frames.append(ss.push(src[:, k * hop:(k + 1) * hop])["bars"].copy())
+            hist = ss.history_device().cpu().numpy()
+            for a in range(depth):                      # k = depth-1 is the newest frame
+                want = frames[k - a] if k - a >= 0 else np.zeros((streams, B), np.float32)
+                assert (hist[:, depth - 1 - a] == want).all(), (k, a)
+        # waveform view of the current window: (int)(sample * 0.02f + offset), fft_lines.c:245
+        win = np.concatenate([np.zeros((streams, n), np.int16), src], axis=1)[:, -n:]
+        off = np.float32((1080 - 30) // 2 + 50)
+        wf = ss.waveform_device(points=2048, scale=0.02, offset=float(off)).cpu().numpy()
+        want = (win.astype(np.float32) * np.float32(0.02) + off).astype(np.int32)
+        assert (wf == want).all()

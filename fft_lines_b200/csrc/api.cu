@@ -280,6 +280,7 @@ struct fftl_stft {
     int* d_bar_seg0;
     float* d_bar_inv;
     int nseg;
+    int mag_bins;                   // highest bin any bar (or the bass bin) reads, + 1
     int num_sms;
     int64_t fast_launches;
     int* d_aux;                     // [2][channels][nf_aux] (w then bass)
@@ -387,6 +388,8 @@ extern "C" int fftl_stft_create(const fftl_config* cfg, int device, fftl_stft** 
         }
         bar_seg0[B] = (int)seg_lo.size();
         h->nseg = (int)seg_lo.size();
+        h->mag_bins = cfg->bass_bin + 1;
+        for (int b = 0; b < B; b++) h->mag_bins = hi[b] > h->mag_bins ? hi[b] : h->mag_bins;
         H_TRY(cudaMalloc(&h->d_seg_bar, sizeof(int) * h->nseg));
         H_TRY(cudaMalloc(&h->d_seg_lo, sizeof(int) * h->nseg));
         H_TRY(cudaMalloc(&h->d_seg_hi, sizeof(int) * h->nseg));
@@ -461,23 +464,33 @@ extern "C" int64_t fftl_stft_num_frames(const fftl_stft* h, int64_t samples)
 extern "C" int64_t fftl_stft_launch_count(const fftl_stft* h) { return h ? h->launches : 0; }
 
 // Fast path (stft_rdif.cuh).  Returns cudaErrorNotSupported when the configuration is not covered.
-template <int F, int HOPQ, bool WIN, int SGW>
+template <int F, int HOPQ, bool WIN, int SGW, int ROWS>
 static cudaError_t launch_rdif(const fftl_stft* h, RdifParams p, int channels, cudaStream_t st)
 {
-    constexpr int MINB = 2; // two CTAs per SM is the design point (128 registers, ~105 KB shared memory)
+    constexpr int MINB = 2; // two CTAs per SM is the design point (128 registers, <= 113 KB shared memory)
     using Sh = RdifShape<4096, F>;
-    size_t smem = Sh::smem_bytes(p.bars_n, p.nseg, p.sg_half);
+    size_t smem = Sh::smem_bytes(p.bars_n, p.nseg, p.sg_half, ROWS);
     if ((smem + 1024) * MINB > 228 * 1024) return cudaErrorNotSupported;
     p.tiles_per_channel = (p.frame_end - p.frame0 + F - 1) / F;
     p.total_tiles = p.tiles_per_channel * channels;
     if (p.total_tiles <= 0) return cudaSuccess;
-    auto kern = stft_bars_rdif_kernel<4096, F, HOPQ, WIN, true, MINB, SGW>;
+    auto kern = stft_bars_rdif_kernel<4096, F, HOPQ, WIN, true, MINB, SGW, ROWS>;
     cudaError_t e = cudaFuncSetAttribute(kern, cudaFuncAttributeMaxDynamicSharedMemorySize, (int)smem);
     if (e != cudaSuccess) return e;
     long long grid = (long long)MINB * h->num_sms;
     if (grid > p.total_tiles) grid = p.total_tiles;
     kern<<<(unsigned)grid, Sh::THREADS, smem, st>>>(p);
     return cudaGetLastError();
+}
+
+// magnitude rows kept: the smallest instantiated count that covers every bin a bar (or the bass bin) reads
+template <int HOPQ, bool WIN, int SGW>
+static cudaError_t launch_rdif_rows(const fftl_stft* h, const RdifParams& p, int channels, cudaStream_t st)
+{
+    if (p.mag_rows <= 1) return launch_rdif<4, HOPQ, WIN, SGW, 1>(h, p, channels, st);
+    if (p.mag_rows <= 4) return launch_rdif<4, HOPQ, WIN, SGW, 4>(h, p, channels, st);
+    if (p.mag_rows <= 7) return launch_rdif<4, HOPQ, WIN, SGW, 7>(h, p, channels, st);
+    return launch_rdif<4, HOPQ, WIN, SGW, 8>(h, p, channels, st);
 }
 
 template <int HOPQ, bool WIN, int SGW>
@@ -512,12 +525,12 @@ template <int HOPQ, bool WIN>
 static cudaError_t launch_rdif_sg(const fftl_stft* h, const RdifParams& p, int channels, cudaStream_t st)
 {
 #ifdef FFTL_GENERIC_SG
-    return launch_rdif<4, HOPQ, WIN, -1>(h, p, channels, st);
+    return launch_rdif_rows<HOPQ, WIN, -1>(h, p, channels, st);
 #endif
     switch (p.sg_half) {
-    case 0: return launch_rdif<4, HOPQ, WIN, 0>(h, p, channels, st);
-    case 3: return launch_rdif<4, HOPQ, WIN, 3>(h, p, channels, st);
-    default: return launch_rdif<4, HOPQ, WIN, -1>(h, p, channels, st);
+    case 0: return launch_rdif_rows<HOPQ, WIN, 0>(h, p, channels, st);
+    case 3: return launch_rdif_rows<HOPQ, WIN, 3>(h, p, channels, st);
+    default: return launch_rdif_rows<HOPQ, WIN, -1>(h, p, channels, st);
     }
 }
 
@@ -559,6 +572,9 @@ static cudaError_t try_rdif(const fftl_stft* h, const StftParams& q, int channel
     p.sg_half = q.sg_half;
     p.strict = q.strict;
     p.bass_bin = q.bass_bin;
+    p.mag_rows = (h->mag_bins + 255) / 256;       // bins < 256*rows are kept; 8 rows also keep bin N/2
+    if (p.mag_rows > 8 || h->mag_bins > 2048) p.mag_rows = 8;
+    p.mag_stride = RdifShape<4096, 4>::mag_stride(p.mag_rows);
     for (int i = 0; i < 4; i++) p.beat_bars[i] = q.beat_bars[i];
     p.zoom = q.zoom;
     p.circle_add = q.circle_add;

@@ -47,6 +47,8 @@ struct RdifParams {
     int* aux_w;
     int* aux_bass;
     int hop, bars_n, nseg, sg_half, strict, bass_bin;
+    int mag_rows;               // 256-bin rows of magnitudes that are kept (bins < 256*mag_rows, + bin N/2 when 8)
+    int mag_stride;             // float2 per frame pair in the magnitude area
     int beat_bars[4];
     float zoom, circle_add;
 };
@@ -106,25 +108,23 @@ template <int N, int F> struct RdifShape {
     // magnitudes: one float2 array per frame pair (.x = even frame, .y = odd frame), padded
     // bin -> bin + bin/16: the 16 lanes of a sub-transform (bins 16 apart) then hit 16 distinct
     // even banks, the other half-warp (odd frame) the odd ones
-    static constexpr int MAGS = padded_size(NB) + 3;
+    // Only the 256-bin rows a configuration reads are kept (mag_rows of them; all 8 plus bin N/2 for full band).
+    __host__ __device__ static constexpr int mag_stride(int mag_rows) { return padded_size(mag_rows >= 8 ? NB : 256 * mag_rows) + 3; }
     __host__ __device__ static size_t tail_bytes(int bars, int nseg) { return (size_t)(nseg + bars) * F * sizeof(float); }
     // per-CTA copies of the tail's tables (the L1 is tiny next to 105 KB of shared memory and is
     // streamed through by the PCM, so table loads from global would pay L2 latency in every tail phase)
     __host__ __device__ static size_t table_bytes(int bars, int nseg, int sg_half)
     {
         int m = 2 * sg_half + 1;
-        return (size_t)nseg * sizeof(int2) + (size_t)(bars + 1) * sizeof(int) + (size_t)bars * sizeof(float) + (size_t)m * m * sizeof(float);
+        return (size_t)nseg * sizeof(int) + (size_t)(bars + 1) * sizeof(int) + (size_t)bars * sizeof(float) + (size_t)m * m * sizeof(float);
     }
-    static size_t smem_bytes(int bars, int nseg, int sg_half)
-    {
-        return smem_bytes(bars, nseg) + table_bytes(bars, nseg, sg_half) + 16;
-    }
-    static size_t smem_bytes(int bars, int nseg)
+    static size_t smem_bytes(int bars, int nseg, int sg_half, int mag_rows)
     {
         // segment sums and raw bars alias the slot area (dead once pass B/C is done)
         size_t slots = (size_t)SLOTS * SLOT * sizeof(float2);
         size_t tail = tail_bytes(bars, nseg);
-        return (slots > tail ? slots : tail) + (size_t)(F / 2) * MAGS * sizeof(float2) + F * 4 * sizeof(int);
+        return (slots > tail ? slots : tail) + (size_t)(F / 2) * mag_stride(mag_rows) * sizeof(float2) + F * 4 * sizeof(int) +
+               table_bytes(bars, nseg, sg_half) + 16;
     }
 };
 
@@ -184,11 +184,13 @@ __device__ __forceinline__ void sg_apply(const float* cf, const float* rw, int m
 }
 
 // SGW: compile-time Savitzky-Golay half width (0 = off, 3 = the default) or -1 for any run-time width.
-template <int N, int F, int HOPQ, bool WINDOWED, bool RESIDENT, int MINB, int SGW>
+// ROWS: number of 256-bin magnitude rows kept (compile time, so unused rows cost nothing).
+template <int N, int F, int HOPQ, bool WINDOWED, bool RESIDENT, int MINB, int SGW, int ROWS>
 __global__ void __launch_bounds__(RdifShape<N, F>::THREADS, MINB) stft_bars_rdif_kernel(const RdifParams p)
 {
     using Sh = RdifShape<N, F>;
-    constexpr int M = Sh::M, SUBG = Sh::SUBG, SLOT = Sh::SLOT, MAGS = Sh::MAGS;
+    constexpr int M = Sh::M, SUBG = Sh::SUBG, SLOT = Sh::SLOT;
+    constexpr int MAGS = Sh::mag_stride(ROWS);
     static_assert(N == 4096, "this instantiation covers N = 4096 (M = 256, two radix-16 sub-passes)");
     static_assert(F == 2 || F == 4, "frames are packed in pairs; the tail moves F floats as one vector");
     constexpr int NX = 16 + HOPQ * (F - 1);          // samples per column per tile
@@ -205,13 +207,13 @@ __global__ void __launch_bounds__(RdifShape<N, F>::THREADS, MINB) stft_bars_rdif
     float* raw = segsum + p.nseg * F;                               // [bars][F]
     float2* mags = reinterpret_cast<float2*>(reinterpret_cast<char*>(smem) + (slot_bytes > tail_bytes ? slot_bytes : tail_bytes)); // [F/2][MAGS]
     int* beat_h = reinterpret_cast<int*>(mags + (F / 2) * MAGS);    // [F][4]
-    int2* t_seg = reinterpret_cast<int2*>(beat_h + F * 4);          // [nseg] (first bin, count)
+    int* t_seg = beat_h + F * 4;                                    // [nseg] padded first bin | count << 16
     int* t_bar0 = reinterpret_cast<int*>(t_seg + p.nseg);           // [bars+1]
     float* t_inv = reinterpret_cast<float*>(t_bar0 + p.bars_n + 1); // [bars]
     float* t_sg = t_inv + p.bars_n;                                 // [(2w+1)^2]
     for (int i = threadIdx.x; i < p.nseg; i += M) {
         const int l = __ldg(p.seg_lo + i);
-        t_seg[i] = make_int2(pad_index(l), __ldg(p.seg_hi + i) - l);
+        t_seg[i] = pad_index(l) | ((__ldg(p.seg_hi + i) - l) << 16);
     }
     for (int i = threadIdx.x; i <= p.bars_n; i += M) t_bar0[i] = __ldg(p.bar_seg0 + i);
     for (int i = threadIdx.x; i < p.bars_n; i += M) t_inv[i] = __ldg(p.bar_inv + i);
@@ -333,16 +335,19 @@ __global__ void __launch_bounds__(RdifShape<N, F>::THREADS, MINB) stft_bars_rdif
 #pragma unroll
                 for (int rr = 0; rr < 16; rr++) {
                     const int kk = Radix<16>::out_index(rr);
-                    float mag = sqrtf(fmaf(v[rr].x, v[rr].x, v[rr].y * v[rr].y));
-                    if (kk < 8) lo_base[2 * 272 * kk] = mag;
-                    else hi_base[2 * 272 * (15 - kk)] = mag;
+                    const int c = kk < 8 ? kk : 15 - kk; // 256-bin row of this output
+                    if (c < ROWS) {                      // rows no bar reads are neither computed nor stored
+                        float mag = sqrtf(fmaf(v[rr].x, v[rr].x, v[rr].y * v[rr].y));
+                        if (kk < 8) lo_base[2 * 272 * c] = mag;
+                        else hi_base[2 * 272 * c] = mag;
+                    }
                 }
             } else {
                 // packed slot (hw 0: residue 0, partner m' = 256-m; hw 1: residue 8, partner m' = 255-m)
                 const int src = hw ? (15 - j) : ((16 - j) & 15);
                 const bool self = (hw == 0) && (j == 0);
 #pragma unroll
-                for (int kk = 0; kk < 8; kk++) {
+                for (int kk = 0; kk < (ROWS < 8 ? ROWS : 8); kk++) {
                     // register holding output kk is rr with out_index(rr) == kk: rr = 4*(kk&3) + (kk>>2)
                     const int rr = 4 * (kk & 3) + (kk >> 2);
                     const int kp = 15 - kk, rp = 4 * (kp & 3) + (kp >> 2);
@@ -356,9 +361,10 @@ __global__ void __launch_bounds__(RdifShape<N, F>::THREADS, MINB) stft_bars_rdif
                     float ar = v[rr].x + pr_, ai = v[rr].y - pi_; // 2 * Xa
                     float br = v[rr].x - pr_, bi = v[rr].y + pi_; // 2i * Xb
                     int bin = 16 * (j + 16 * kk) + (hw ? 8 : 0);
-                    mg2[pad_index(bin)] = make_float2(0.5f * sqrtf(fmaf(ar, ar, ai * ai)), 0.5f * sqrtf(fmaf(br, br, bi * bi)));
+                    const float2 mm = make_float2(0.5f * sqrtf(fmaf(ar, ar, ai * ai)), 0.5f * sqrtf(fmaf(br, br, bi * bi)));
+                    mg2[pad_index(bin)] = mm;
                 }
-                if (self) {
+                if (self && ROWS >= 8) {
                     // m = 128 (bin N/2) is its own partner: Z[128] = Xa[N/2] + i Xb[N/2], both real
                     const int rr = 4 * (8 & 3) + (8 >> 2);
                     mg2[pad_index(N / 2)] = make_float2(fabsf(v[rr].x), fabsf(v[rr].y));
@@ -370,9 +376,9 @@ __global__ void __launch_bounds__(RdifShape<N, F>::THREADS, MINB) stft_bars_rdif
         // segments are at most 8 bins long and never cross a multiple of 16, so a segment is 8 consecutive
         // padded positions at most
         for (int sgi = t; sgi < p.nseg; sgi += M) {
-            const int2 sd = t_seg[sgi];
-            const int cnt = sd.y;
-            const float2* m0 = mags + sd.x;
+            const int sd = t_seg[sgi];
+            const int cnt = sd >> 16;
+            const float2* m0 = mags + (sd & 0xffff);
             float acc[F];
 #pragma unroll
             for (int f = 0; f < F; f++) acc[f] = 0.0f;

@@ -15,6 +15,7 @@
 #include "kernels.cuh"
 #include "stft_rdif.cuh"
 #include "stft_rdif3.cuh"
+#include "stft_rdif_ws.cuh"
 #include "stream.cuh"
 #include "../../include/fft_calculate.h"
 #include "../../include/beatDetector.h"
@@ -493,6 +494,24 @@ static cudaError_t launch_rdif_rows(const fftl_stft* h, const RdifParams& p, int
     return launch_rdif<4, HOPQ, WIN, SGW, 8>(h, p, channels, st);
 }
 
+template <int HOPQ, bool WIN, int SGW, int ROWS>
+static cudaError_t launch_rdif_ws(const fftl_stft* h, RdifParams p, int channels, cudaStream_t st)
+{
+    using Sh = RdifWsShape<ROWS>;
+    size_t smem = Sh::smem_bytes(p.bars_n, p.nseg, p.sg_half);
+    if (smem > 227 * 1024) return cudaErrorNotSupported;
+    p.tiles_per_channel = (p.frame_end - p.frame0 + Sh::F - 1) / Sh::F;
+    p.total_tiles = p.tiles_per_channel * channels;
+    if (p.total_tiles <= 0) return cudaSuccess;
+    auto kern = stft_bars_rdif_ws_kernel<HOPQ, WIN, SGW, ROWS>;
+    cudaError_t e = cudaFuncSetAttribute(kern, cudaFuncAttributeMaxDynamicSharedMemorySize, (int)smem);
+    if (e != cudaSuccess) return e;
+    long long grid = h->num_sms; // one persistent CTA per SM
+    if (grid > p.total_tiles) grid = p.total_tiles;
+    kern<<<(unsigned)grid, Sh::THREADS, smem, st>>>(p);
+    return cudaGetLastError();
+}
+
 template <int HOPQ, bool WIN, int SGW>
 static cudaError_t launch_rdif3(const fftl_stft* h, RdifParams p, int channels, cudaStream_t st)
 {
@@ -579,6 +598,11 @@ static cudaError_t try_rdif(const fftl_stft* h, const StftParams& q, int channel
     p.zoom = q.zoom;
     p.circle_add = q.circle_add;
     const bool win = q.window != nullptr;
+    static const bool usews = getenv("FFTL_RDIF_WS") != nullptr; // developer A/B switch (experimental: HOPQ 2, SG 3)
+    if (usews && hopq == 2 && p.sg_half == 3 && win) {
+        cudaError_t ew = p.mag_rows <= 7 ? launch_rdif_ws<2, true, 3, 7>(h, p, channels, st) : launch_rdif_ws<2, true, 3, 8>(h, p, channels, st);
+        if (ew != cudaErrorNotSupported) return ew;
+    }
     static const bool use3 = getenv("FFTL_RDIF3") != nullptr; // developer A/B switch
     if (use3) {
         cudaError_t e3;

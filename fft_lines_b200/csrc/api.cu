@@ -16,6 +16,7 @@
 #include "stft_rdif.cuh"
 #include "stft_rdif3.cuh"
 #include "stft_rdif_ws.cuh"
+#include "stft_rdif_ws2.cuh"
 #include "stream.cuh"
 #include "../../include/fft_calculate.h"
 #include "../../include/beatDetector.h"
@@ -495,6 +496,24 @@ static cudaError_t launch_rdif_rows(const fftl_stft* h, const RdifParams& p, int
 }
 
 template <int HOPQ, bool WIN, int SGW, int ROWS>
+static cudaError_t launch_rdif_ws2(const fftl_stft* h, RdifParams p, int channels, cudaStream_t st)
+{
+    using Sh = RdifWs2Shape<ROWS>;
+    size_t smem = Sh::smem_bytes(p.bars_n, p.nseg, p.sg_half);
+    if (smem > 227 * 1024) return cudaErrorNotSupported;
+    p.tiles_per_channel = (p.frame_end - p.frame0 + Sh::F - 1) / Sh::F;
+    p.total_tiles = p.tiles_per_channel * channels;
+    if (p.total_tiles <= 0) return cudaSuccess;
+    auto kern = stft_bars_rdif_ws2_kernel<HOPQ, WIN, SGW, ROWS>;
+    cudaError_t e = cudaFuncSetAttribute(kern, cudaFuncAttributeMaxDynamicSharedMemorySize, (int)smem);
+    if (e != cudaSuccess) return e;
+    long long grid = h->num_sms; // one persistent CTA per SM, two transform groups each
+    if (grid * 2 > p.total_tiles) grid = (p.total_tiles + 1) / 2;
+    kern<<<(unsigned)grid, Sh::THREADS, smem, st>>>(p);
+    return cudaGetLastError();
+}
+
+template <int HOPQ, bool WIN, int SGW, int ROWS>
 static cudaError_t launch_rdif_ws(const fftl_stft* h, RdifParams p, int channels, cudaStream_t st)
 {
     using Sh = RdifWsShape<ROWS>;
@@ -598,6 +617,11 @@ static cudaError_t try_rdif(const fftl_stft* h, const StftParams& q, int channel
     p.zoom = q.zoom;
     p.circle_add = q.circle_add;
     const bool win = q.window != nullptr;
+    static const bool usews2 = getenv("FFTL_RDIF_WS2") != nullptr; // developer A/B switch (experimental: HOPQ 2, SG 3, Hann)
+    if (usews2 && hopq == 2 && p.sg_half == 3 && win) {
+        cudaError_t ew = p.mag_rows <= 7 ? launch_rdif_ws2<2, true, 3, 7>(h, p, channels, st) : launch_rdif_ws2<2, true, 3, 8>(h, p, channels, st);
+        if (ew != cudaErrorNotSupported) return ew;
+    }
     static const bool usews = getenv("FFTL_RDIF_WS") != nullptr; // developer A/B switch (experimental: HOPQ 2, SG 3)
     if (usews && hopq == 2 && p.sg_half == 3 && win) {
         cudaError_t ew = p.mag_rows <= 7 ? launch_rdif_ws<2, true, 3, 7>(h, p, channels, st) : launch_rdif_ws<2, true, 3, 8>(h, p, channels, st);

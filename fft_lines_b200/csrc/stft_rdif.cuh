@@ -183,6 +183,114 @@ __device__ __forceinline__ void sg_apply(const float* cf, const float* rw, int m
     }
 }
 
+// Row of the Savitzky-Golay matrix and first raw bar it applies to, for output bar b of B (half width w):
+// interior bars use the centre row on [b-w, b+w]; the w bars at either edge use the edge rows of the
+// polynomial fit over the first / last 2w+1 bars (scipy's mode="interp").
+__device__ __forceinline__ void sg_row(int b, int B, int w, int& row, int& base)
+{
+    base = min(max(b - w, 0), B - (2 * w + 1));
+    row = b - base;
+}
+
+// Tail, last step: Savitzky-Golay -> zoom -> heights of the tile's F frames (fft_lines.c:195-208), done by
+// `nthreads` threads (this one is number t).  The float multiply and add are the explicit _rn forms so
+// that the fast and the careful branch round alike (a frame can sit in an edge tile of one shard and in
+// an interior tile of the full run).
+template <int F, int SGW>
+__device__ __forceinline__ void rdif_emit_bars(const RdifParams& p, const float* raw, const float* t_sg, int t, int nthreads, int ch, long long f0)
+{
+    const int B = p.bars_n;
+    const int w = SGW >= 0 ? SGW : p.sg_half, m = 2 * w + 1;
+    // frames of this tile that are emitted: [e_lo, e_hi)
+    const long long dlo = p.frame_emit - f0, dhi = p.frame_end - f0;
+    const long long o0 = ((long long)ch * p.nf_emit + (f0 - p.frame_emit)) * B;
+    if (dlo <= 0 && dhi >= F && p.bars_i32 == nullptr) {
+        // every frame of the tile is emitted, float heights only: nothing to predicate
+#pragma unroll 1
+        for (int b = t; b < B; b += nthreads) {
+            float y[F];
+            if (w == 0) FrameVec<F>::load(raw + b * F, y);
+            else {
+                int row, base;
+                sg_row(b, B, w, row, base);
+                sg_apply<F, (SGW > 0 ? 2 * SGW + 1 : -1)>(t_sg + row * m, raw + base * F, m, y);
+            }
+            float* ob = p.bars + (o0 + b);
+#pragma unroll
+            for (int f = 0; f < F; f++) ob[f * B] = __fadd_rn(__fmul_rn(y[f], p.zoom), p.circle_add);
+        }
+        return;
+    }
+    const int e_lo = dlo > 0 ? (dlo < F ? (int)dlo : F) : 0;
+    const int e_hi = dhi < F ? (dhi > 0 ? (int)dhi : 0) : F;
+    const int cadd = (int)p.circle_add;
+#pragma unroll 1
+    for (int b = t; b < B; b += nthreads) {
+        float y[F];
+        if (w == 0) FrameVec<F>::load(raw + b * F, y);
+        else {
+            int row, base;
+            sg_row(b, B, w, row, base);
+            sg_apply<F, (SGW > 0 ? 2 * SGW + 1 : -1)>(t_sg + row * m, raw + base * F, m, y);
+        }
+        float* ob = p.bars + (o0 + b);
+        int* oi = p.bars_i32 ? p.bars_i32 + (o0 + b) : nullptr;
+#pragma unroll
+        for (int f = 0; f < F; f++) {
+            y[f] = __fmul_rn(y[f], p.zoom);
+            if (f >= e_lo && f < e_hi) {
+                ob[f * B] = __fadd_rn(y[f], p.circle_add);
+                if (oi) oi[f * B] = wrap_add(trunc_i32(y[f], p.strict), cadd);
+            }
+        }
+    }
+}
+
+// Band energy w = (h[b0]+h[b1]+h[b2]+h[b3])/4 (fft_lines.c:281) and bass = (int)|X[bass_bin]|
+// (beatDetector.c:53) of the tile's F frames, by threads 0..4F-1 of one warp: thread (f, q) redoes the
+// integer height of beat bar q for frame f with the arithmetic of rdif_emit_bars, a 4-lane shuffle sums them.
+// mags: the tile's magnitude area ([F/2][mag_stride] float2).
+template <int F, int SGW>
+__device__ __forceinline__ void rdif_emit_beat(const RdifParams& p, const float* raw, const float* t_sg, const float2* mags, int mag_stride,
+                                               int t, int ch, long long f0)
+{
+    if (p.aux_w == nullptr || t >= 4 * F) return;
+    constexpr unsigned MASK = (4 * F >= 32) ? 0xffffffffu : ((1u << (4 * F)) - 1u);
+    const int B = p.bars_n;
+    const int w = SGW >= 0 ? SGW : p.sg_half, m = 2 * w + 1;
+    const int f = t >> 2, q = t & 3;
+    const int b = p.beat_bars[q];
+    float y;
+    if (w == 0) y = raw[b * F + f];
+    else {
+        int row, base;
+        sg_row(b, B, w, row, base);
+        const float* cf = t_sg + row * m;
+        const float* rw = raw + base * F + f;
+        y = 0.0f;
+        if (SGW > 0) {
+#pragma unroll
+            for (int k = 0; k < 2 * SGW + 1; k++) y = fmaf(cf[k], rw[k * F], y);
+        } else {
+#pragma unroll 1
+            for (int k = 0; k < m; k++) y = fmaf(cf[k], rw[k * F], y);
+        }
+    }
+    y = __fmul_rn(y, p.zoom);
+    unsigned h = (unsigned)wrap_add(trunc_i32(y, p.strict), (int)p.circle_add);
+    h += __shfl_xor_sync(MASK, h, 1);
+    h += __shfl_xor_sync(MASK, h, 2);
+    const long long fr = f0 + f;
+    if (q == 0 && fr < p.frame_end) {
+        const long long o = (long long)ch * p.nf_aux + (fr - p.aux_base);
+        p.aux_w[o] = (int)h / 4;
+        if (mags) { // null: the caller has written the bass already (its magnitude buffer is gone by now)
+            const float2 mb = mags[(f >> 1) * mag_stride + pad_index(p.bass_bin)];
+            p.aux_bass[o] = trunc_i32((f & 1) ? mb.y : mb.x, p.strict);
+        }
+    }
+}
+
 // SGW: compile-time Savitzky-Golay half width (0 = off, 3 = the default) or -1 for any run-time width.
 // ROWS: number of 256-bin magnitude rows kept (compile time, so unused rows cost nothing).
 template <int N, int F, int HOPQ, bool WINDOWED, bool RESIDENT, int MINB, int SGW, int ROWS>
@@ -240,22 +348,6 @@ __global__ void __launch_bounds__(RdifShape<N, F>::THREADS, MINB) stft_bars_rdif
         for (int r = 1; r < 16; r++) twc[r] = __ldg(p.twm + j * r);
     }
 
-    long long prev_f0 = -1; // tile whose band energy / bass are still to be written (after the next barrier)
-    int prev_ch = 0;
-    auto flush_aux = [&]() {
-        if (t < F && p.aux_w && prev_f0 >= 0) {
-            const long long fr = prev_f0 + t;
-            if (fr < p.frame_end) {
-                const int* h4 = beat_h + 4 * t;
-                int sum = wrap_add(wrap_add(h4[0], h4[1]), wrap_add(h4[2], h4[3]));
-                const float2 mb = mags[(t >> 1) * MAGS + pad_index(p.bass_bin)];
-                long long o = (long long)prev_ch * p.nf_aux + (fr - p.aux_base);
-                p.aux_w[o] = sum / 4;                                              // fft_lines.c:281
-                p.aux_bass[o] = trunc_i32((t & 1) ? mb.y : mb.x, p.strict);        // beatDetector.c:53
-            }
-        }
-    };
-
     for (long long tile = blockIdx.x; tile < p.total_tiles; tile += gridDim.x) {
         const int ch = (int)(tile / p.tiles_per_channel);
         const long long f0 = p.frame0 + (tile % p.tiles_per_channel) * F; // first frame of the tile (even)
@@ -272,8 +364,7 @@ __global__ void __launch_bounds__(RdifShape<N, F>::THREADS, MINB) stft_bars_rdif
             for (int r = 0; r < NX; r++) xr[r] = (s0 + t + (long long)r * M < p.samples) ? (float)xp[r * M] : 0.0f;
         }
         if (!late_alias) {
-            __syncthreads(); // previous tile's tail is done with the aliased slots and has published beat_h
-            flush_aux();
+            __syncthreads(); // previous tile's tail is done with the aliased slots
         }
         if (!RESIDENT) {
             if (WINDOWED) {
@@ -286,8 +377,7 @@ __global__ void __launch_bounds__(RdifShape<N, F>::THREADS, MINB) stft_bars_rdif
 #pragma unroll
         for (int pr = 0; pr < F / 2; pr++) {
             if (late_alias && pr == F / 2 - 1) {
-                __syncthreads(); // previous tile's tail is done with the last pair's slots and has published beat_h
-                flush_aux();
+                __syncthreads(); // previous tile's tail is done with the last pair's slots
             }
             float2* ps = slots + pr * 16 * SLOT + pad_index(t);
             float y0[2], y8[2];
@@ -412,57 +502,12 @@ __global__ void __launch_bounds__(RdifShape<N, F>::THREADS, MINB) stft_bars_rdif
             FrameVec<F>::store(raw + b * F, acc);
         }
         __syncthreads();
-        {
-            const int w = SGW >= 0 ? SGW : p.sg_half, m = 2 * w + 1;
-            // frames of this tile that are emitted: [e_lo, e_hi)
-            const long long dlo = p.frame_emit - f0, dhi = p.frame_end - f0;
-            const int e_lo = dlo > 0 ? (dlo < F ? (int)dlo : F) : 0;
-            const int e_hi = dhi < F ? (dhi > 0 ? (int)dhi : 0) : F;
-            const long long o0 = ((long long)ch * p.nf_emit + (f0 - p.frame_emit)) * B;
-            const bool want_int = (p.bars_i32 != nullptr) || (p.aux_w != nullptr);
-#pragma unroll 1
-            for (int b = t; b < B; b += M) {
-                float y[F];
-                if (w == 0) FrameVec<F>::load(raw + b * F, y);
-                else {
-                    int row, base;
-                    if (b < w) { row = b; base = 0; }
-                    else if (b >= B - w) { row = m - (B - b); base = B - m; }
-                    else { row = w; base = b - w; }
-                    sg_apply<F, (SGW > 0 ? 2 * SGW + 1 : -1)>(t_sg + row * m, raw + base * F, m, y);
-                }
-                float* ob = p.bars + (o0 + b);
-#pragma unroll
-                for (int f = 0; f < F; f++) {
-                    y[f] *= p.zoom;
-                    if (f >= e_lo && f < e_hi) ob[f * B] = y[f] + p.circle_add;
-                }
-                if (want_int) {
-                    const bool isbeat = (b == p.beat_bars[0]) | (b == p.beat_bars[1]) | (b == p.beat_bars[2]) | (b == p.beat_bars[3]);
-                    if (p.bars_i32 || isbeat) {
-                        int* oi = p.bars_i32 ? p.bars_i32 + (o0 + b) : nullptr;
-                        const int cadd = (int)p.circle_add;
-#pragma unroll
-                        for (int f = 0; f < F; f++) {
-                            const int ih = wrap_add(trunc_i32(y[f], p.strict), cadd);
-                            if (oi && f >= e_lo && f < e_hi) oi[f * B] = ih;
-                            if (isbeat) {
-#pragma unroll
-                                for (int q = 0; q < 4; q++)
-                                    if (b == p.beat_bars[q]) beat_h[f * 4 + q] = ih;
-                            }
-                        }
-                    }
-                }
-            }
-        }
+        // band energy / bass first (16 lanes of warp 0; the magnitudes are still in place), then the heights
+        rdif_emit_beat<F, SGW>(p, raw, t_sg, mags, MAGS, t, ch, f0);
+        rdif_emit_bars<F, SGW>(p, raw, t_sg, t, M, ch, f0);
         // No barrier here: the next tile's pass A starts at once; the barrier that protects the aliased
-        // buffers and publishes beat_h is the one inside (late_alias) or in front of (otherwise) its pass A.
-        prev_f0 = f0;
-        prev_ch = ch;
+        // buffers is the one inside (late_alias) or in front of (otherwise) its pass A.
     }
-    __syncthreads();
-    flush_aux();
 }
 
 } // namespace fftl

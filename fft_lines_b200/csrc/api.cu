@@ -822,13 +822,22 @@ extern "C" int fftl_stft_run(fftl_stft* h, const int16_t* pcm, int32_t channels,
         h->d_aux = (int*)pv;
         if (rc) return rc;
     }
-    // chunk size: ~64 MiB of bar output per slot, at least 512 frames, even
-    static const long long chunk_mib = getenv("FFTL_CHUNK_MIB") ? atoll(getenv("FFTL_CHUNK_MIB")) : 64; // developer knob
+    // chunk size: ~32 MiB of bar output per slot (measured best on c2: 16-32 MiB tie, 8 and 64 lose 5-10 %), at least 512 frames, even
+    static const long long chunk_mib = getenv("FFTL_CHUNK_MIB") ? atoll(getenv("FFTL_CHUNK_MIB")) : 32; // developer knob
     int64_t chunk = (int64_t)(chunk_mib << 20) / ((int64_t)channels * B * 4);
     if (chunk < 512) chunk = 512;
     if (chunk > fe - warm) chunk = fe - warm;
     chunk += chunk & 1;
     const int64_t nf_total = fe - fb;
+    // both staging slots get their full-chunk size up front: growing one later would free a buffer the
+    // pipeline may still be using (cudaFree waits for the device, so it is safe, but it drains the pipe)
+    for (int sl = 0; sl < 2; sl++) {
+        if ((rc = ensure_bytes(&h->d_stage[sl][0], &h->stage_bytes[sl][0], sizeof(int16_t) * (size_t)channels * (size_t)(chunk * hop + n)))) return rc;
+        if ((rc = ensure_bytes(&h->d_stage[sl][1], &h->stage_bytes[sl][1], sizeof(float) * (size_t)channels * (size_t)chunk * B))) return rc;
+        if (bars_i32 && (rc = ensure_bytes(&h->d_stage[sl][2], &h->stage_bytes[sl][2], sizeof(int32_t) * (size_t)channels * (size_t)chunk * B))) return rc;
+        if (beat && (rc = ensure_bytes(&h->d_stage[sl][3], &h->stage_bytes[sl][3], sizeof(fftl_beat) * (size_t)channels * (size_t)chunk))) return rc;
+    }
+    static const int dbg_skip = getenv("FFTL_E2E_SKIP") ? atoi(getenv("FFTL_E2E_SKIP")) : 0; // developer knob: 1 = no H2D, 2 = no D2H
     int slot = 0;
     int64_t nchunks = 0;
     for (int64_t a = warm; a < fe; a += chunk, slot ^= 1, nchunks++) {
@@ -844,15 +853,14 @@ extern "C" int fftl_stft_run(fftl_stft* h, const int16_t* pcm, int32_t channels,
         size_t pcm_bytes = sizeof(int16_t) * (size_t)channels * span;
         size_t bars_bytes = sizeof(float) * (size_t)channels * (size_t)(ne > 0 ? ne : 1) * B;
         size_t beat_bytes = sizeof(fftl_beat) * (size_t)channels * (size_t)(ne > 0 ? ne : 1);
-        // the slot's previous D2H must be finished before its buffers are reused
-        if (nchunks >= 2) CUDA_TRY(cudaEventSynchronize(h->ev_d2h[slot]));
         if ((rc = ensure_bytes(&h->d_stage[slot][0], &h->stage_bytes[slot][0], pcm_bytes))) return rc;
         if ((rc = ensure_bytes(&h->d_stage[slot][1], &h->stage_bytes[slot][1], bars_bytes))) return rc;
         if (bars_i32 && (rc = ensure_bytes(&h->d_stage[slot][2], &h->stage_bytes[slot][2], bars_bytes))) return rc;
         if (beat && (rc = ensure_bytes(&h->d_stage[slot][3], &h->stage_bytes[slot][3], beat_bytes))) return rc;
         int16_t* d_pcm = (int16_t*)h->d_stage[slot][0];
         // H2D (the compute that last read this slot's pcm finished before its D2H did)
-        if (interleaved) {
+        if (dbg_skip == 1) {
+        } else if (interleaved) {
             CUDA_TRY(cudaMemcpyAsync(d_pcm, pcm + s0 * channels, pcm_bytes, cudaMemcpyHostToDevice, h->s_h2d));
         } else {
             // one strided copy for all channels (1024 streams must not become 1024 memcpy calls)
@@ -861,6 +869,9 @@ extern "C" int fftl_stft_run(fftl_stft* h, const int16_t* pcm, int32_t channels,
         }
         CUDA_TRY(cudaEventRecord(h->ev_h2d[slot], h->s_h2d));
         CUDA_TRY(cudaStreamWaitEvent(h->stream, h->ev_h2d[slot], 0));
+        // the slot's previous D2H (two chunks back) must have drained its output buffers; waiting on the
+        // device keeps the host enqueueing ahead, so the H2D engine never idles behind a D2H
+        if (nchunks >= 2) CUDA_TRY(cudaStreamWaitEvent(h->stream, h->ev_d2h[slot], 0));
         // kernels: device pcm starts at sample s0, i.e. frame a
         {
             const int16_t* base = interleaved ? d_pcm - s0 * channels : d_pcm - s0;
@@ -880,7 +891,7 @@ extern "C" int fftl_stft_run(fftl_stft* h, const int16_t* pcm, int32_t channels,
         // next H2D into the other slot may start now; it must not overwrite this
         // slot's pcm until this compute is done -> h2d stream waits on ev_comp of the slot it reuses
         CUDA_TRY(cudaStreamWaitEvent(h->s_h2d, h->ev_comp[slot ^ 1], 0));
-        if (ne > 0) {
+        if (ne > 0 && dbg_skip != 2) {
             // host [ch][nf_total][B] <- device [ch][ne][B]: one strided copy per output
             const size_t off_h = (size_t)(ea - fb) * B;
             CUDA_TRY(cudaMemcpy2DAsync(bars + off_h, sizeof(float) * nf_total * B, h->d_stage[slot][1], sizeof(float) * ne * B,

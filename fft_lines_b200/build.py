@@ -13,7 +13,7 @@ HERE = os.path.dirname(os.path.abspath(__file__))
 CSRC = os.path.join(HERE, "csrc")
 LIB = os.path.join(HERE, "libfftlines_cuda.so")
 SOURCES = ["api.cu"]
-HEADERS = ["kernels.cuh", "fft_device.cuh", "stft_rdif.cuh", "stft_rdif3.cuh", "stft_rdif_ws.cuh", "stft_rdif_ws2.cuh", "stream.cuh", "../../include/fftlines.h", "../../include/fft_calculate.h",
+HEADERS = ["kernels.cuh", "fft_device.cuh", "stft_rdif.cuh", "stft_rdif_ws2.cuh", "stream.cuh", "../../include/fftlines.h", "../../include/fft_calculate.h",
            "../../include/beatDetector.h", "../../include/fftl_complex.h"]
 
 

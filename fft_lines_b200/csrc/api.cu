@@ -14,8 +14,6 @@
 
 #include "kernels.cuh"
 #include "stft_rdif.cuh"
-#include "stft_rdif3.cuh"
-#include "stft_rdif_ws.cuh"
 #include "stft_rdif_ws2.cuh"
 #include "stream.cuh"
 #include "../../include/fft_calculate.h"
@@ -276,9 +274,8 @@ struct fftl_stft {
     float* d_sg;
     // fast path (stft_rdif.cuh): sub-transform twiddles and the balanced binning segments
     float2* d_twm;
-    int* d_seg_bar;
-    int* d_seg_lo;
-    int* d_seg_hi;
+    int* d_seg_packed;
+    bool seg_packable;
     int* d_bar_seg0;
     float* d_bar_inv;
     int nseg;
@@ -373,7 +370,7 @@ extern "C" int fftl_stft_create(const fftl_config* cfg, int device, fftl_stft** 
         // of 16 (so a segment is contiguous in the padded magnitude array); partial sums are combined in a
         // fixed order, which keeps the result deterministic
         const int L = 8;
-        std::vector<int> seg_bar, seg_lo, seg_hi, bar_seg0(B + 1);
+        std::vector<int> seg_lo, seg_hi, bar_seg0(B + 1);
         std::vector<float> bar_inv(B);
         for (int b = 0; b < B; b++) {
             bar_seg0[b] = (int)seg_lo.size();
@@ -381,7 +378,6 @@ extern "C" int fftl_stft_create(const fftl_config* cfg, int device, fftl_stft** 
                 int e = k + L < hi[b] ? k + L : hi[b];
                 int block_end = (k / 16 + 1) * 16;
                 if (e > block_end) e = block_end;
-                seg_bar.push_back(b);
                 seg_lo.push_back(k);
                 seg_hi.push_back(e);
                 k = e;
@@ -392,14 +388,18 @@ extern "C" int fftl_stft_create(const fftl_config* cfg, int device, fftl_stft** 
         h->nseg = (int)seg_lo.size();
         h->mag_bins = cfg->bass_bin + 1;
         for (int b = 0; b < B; b++) h->mag_bins = hi[b] > h->mag_bins ? hi[b] : h->mag_bins;
-        H_TRY(cudaMalloc(&h->d_seg_bar, sizeof(int) * h->nseg));
-        H_TRY(cudaMalloc(&h->d_seg_lo, sizeof(int) * h->nseg));
-        H_TRY(cudaMalloc(&h->d_seg_hi, sizeof(int) * h->nseg));
+        // work list of the segment sums in bin order, packed for the fast kernel
+        std::vector<int> packed(h->nseg);
+        h->seg_packable = h->nseg < (1 << 15);
+        for (int i = 0; i < h->nseg; i++) {
+            const int k = i, pl = pad_index(seg_lo[k]);
+            if (pl >= (1 << 13)) h->seg_packable = false;
+            packed[i] = FFTL_SEG_PACK(pl, seg_hi[k] - seg_lo[k], k);
+        }
+        H_TRY(cudaMalloc(&h->d_seg_packed, sizeof(int) * h->nseg));
         H_TRY(cudaMalloc(&h->d_bar_seg0, sizeof(int) * (B + 1)));
         H_TRY(cudaMalloc(&h->d_bar_inv, sizeof(float) * B));
-        H_TRY(cudaMemcpy(h->d_seg_bar, seg_bar.data(), sizeof(int) * h->nseg, cudaMemcpyHostToDevice));
-        H_TRY(cudaMemcpy(h->d_seg_lo, seg_lo.data(), sizeof(int) * h->nseg, cudaMemcpyHostToDevice));
-        H_TRY(cudaMemcpy(h->d_seg_hi, seg_hi.data(), sizeof(int) * h->nseg, cudaMemcpyHostToDevice));
+        H_TRY(cudaMemcpy(h->d_seg_packed, packed.data(), sizeof(int) * h->nseg, cudaMemcpyHostToDevice));
         H_TRY(cudaMemcpy(h->d_bar_seg0, bar_seg0.data(), sizeof(int) * (B + 1), cudaMemcpyHostToDevice));
         H_TRY(cudaMemcpy(h->d_bar_inv, bar_inv.data(), sizeof(float) * B, cudaMemcpyHostToDevice));
         std::vector<float2> twm;
@@ -435,9 +435,7 @@ extern "C" void fftl_stft_destroy(fftl_stft* h)
     cudaFree(h->d_sg);
     cudaFree(h->d_aux);
     cudaFree(h->d_twm);
-    cudaFree(h->d_seg_bar);
-    cudaFree(h->d_seg_lo);
-    cudaFree(h->d_seg_hi);
+    cudaFree(h->d_seg_packed);
     cudaFree(h->d_bar_seg0);
     cudaFree(h->d_bar_inv);
     for (int i = 0; i < 2; i++)
@@ -513,51 +511,6 @@ static cudaError_t launch_rdif_ws2(const fftl_stft* h, RdifParams p, int channel
     return cudaGetLastError();
 }
 
-template <int HOPQ, bool WIN, int SGW, int ROWS>
-static cudaError_t launch_rdif_ws(const fftl_stft* h, RdifParams p, int channels, cudaStream_t st)
-{
-    using Sh = RdifWsShape<ROWS>;
-    size_t smem = Sh::smem_bytes(p.bars_n, p.nseg, p.sg_half);
-    if (smem > 227 * 1024) return cudaErrorNotSupported;
-    p.tiles_per_channel = (p.frame_end - p.frame0 + Sh::F - 1) / Sh::F;
-    p.total_tiles = p.tiles_per_channel * channels;
-    if (p.total_tiles <= 0) return cudaSuccess;
-    auto kern = stft_bars_rdif_ws_kernel<HOPQ, WIN, SGW, ROWS>;
-    cudaError_t e = cudaFuncSetAttribute(kern, cudaFuncAttributeMaxDynamicSharedMemorySize, (int)smem);
-    if (e != cudaSuccess) return e;
-    long long grid = h->num_sms; // one persistent CTA per SM
-    if (grid > p.total_tiles) grid = p.total_tiles;
-    kern<<<(unsigned)grid, Sh::THREADS, smem, st>>>(p);
-    return cudaGetLastError();
-}
-
-template <int HOPQ, bool WIN, int SGW>
-static cudaError_t launch_rdif3(const fftl_stft* h, RdifParams p, int channels, cudaStream_t st)
-{
-    using Sh = Rdif3Shape;
-    size_t smem = Sh::smem_bytes(p.bars_n, p.nseg, p.sg_half);
-    if ((smem + 1024) * 3 > 228 * 1024) return cudaErrorNotSupported; // three CTAs per SM is the design point
-    p.tiles_per_channel = (p.frame_end - p.frame0 + Sh::F - 1) / Sh::F;
-    p.total_tiles = p.tiles_per_channel * channels;
-    if (p.total_tiles <= 0) return cudaSuccess;
-    auto kern = stft_bars_rdif3_kernel<HOPQ, WIN, SGW>;
-    cudaError_t e = cudaFuncSetAttribute(kern, cudaFuncAttributeMaxDynamicSharedMemorySize, (int)smem);
-    if (e != cudaSuccess) return e;
-    long long grid = 3ll * h->num_sms;
-    if (grid > p.total_tiles) grid = p.total_tiles;
-    kern<<<(unsigned)grid, 256, smem, st>>>(p);
-    return cudaGetLastError();
-}
-
-template <int HOPQ, bool WIN>
-static cudaError_t launch_rdif3_sg(const fftl_stft* h, const RdifParams& p, int channels, cudaStream_t st)
-{
-    switch (p.sg_half) {
-    case 0: return launch_rdif3<HOPQ, WIN, 0>(h, p, channels, st);
-    case 3: return launch_rdif3<HOPQ, WIN, 3>(h, p, channels, st);
-    default: return launch_rdif3<HOPQ, WIN, -1>(h, p, channels, st);
-    }
-}
 
 template <int HOPQ, bool WIN>
 static cudaError_t launch_rdif_sg(const fftl_stft* h, const RdifParams& p, int channels, cudaStream_t st)
@@ -578,7 +531,7 @@ static cudaError_t try_rdif(const fftl_stft* h, const StftParams& q, int channel
     if (c.n != 4096 || q.sample_stride != 1 || (c.hop % 256) != 0) return cudaErrorNotSupported;
     const int hopq = c.hop / 256;
     if (hopq != 1 && hopq != 2 && hopq != 4) return cudaErrorNotSupported;
-    if (getenv("FFTL_DISABLE_RDIF")) return cudaErrorNotSupported;
+    if (getenv("FFTL_DISABLE_RDIF") || !h->seg_packable) return cudaErrorNotSupported;
     RdifParams p;
     memset(&p, 0, sizeof(p));
     p.pcm = q.pcm;
@@ -594,9 +547,7 @@ static cudaError_t try_rdif(const fftl_stft* h, const StftParams& q, int channel
     p.window = q.window;
     p.tw = q.tw;
     p.twm = h->d_twm;
-    p.seg_bar = h->d_seg_bar;
-    p.seg_lo = h->d_seg_lo;
-    p.seg_hi = h->d_seg_hi;
+    p.seg_packed = h->d_seg_packed;
     p.bar_seg0 = h->d_bar_seg0;
     p.bar_inv = h->d_bar_inv;
     p.sg = q.sg;
@@ -621,21 +572,6 @@ static cudaError_t try_rdif(const fftl_stft* h, const StftParams& q, int channel
     if (usews2 && hopq == 2 && p.sg_half == 3 && win) {
         cudaError_t ew = p.mag_rows <= 7 ? launch_rdif_ws2<2, true, 3, 7>(h, p, channels, st) : launch_rdif_ws2<2, true, 3, 8>(h, p, channels, st);
         if (ew != cudaErrorNotSupported) return ew;
-    }
-    static const bool usews = getenv("FFTL_RDIF_WS") != nullptr; // developer A/B switch (experimental: HOPQ 2, SG 3)
-    if (usews && hopq == 2 && p.sg_half == 3 && win) {
-        cudaError_t ew = p.mag_rows <= 7 ? launch_rdif_ws<2, true, 3, 7>(h, p, channels, st) : launch_rdif_ws<2, true, 3, 8>(h, p, channels, st);
-        if (ew != cudaErrorNotSupported) return ew;
-    }
-    static const bool use3 = getenv("FFTL_RDIF3") != nullptr; // developer A/B switch
-    if (use3) {
-        cudaError_t e3;
-        switch (hopq) {
-        case 1: e3 = win ? launch_rdif3_sg<1, true>(h, p, channels, st) : launch_rdif3_sg<1, false>(h, p, channels, st); break;
-        case 2: e3 = win ? launch_rdif3_sg<2, true>(h, p, channels, st) : launch_rdif3_sg<2, false>(h, p, channels, st); break;
-        default: e3 = win ? launch_rdif3_sg<4, true>(h, p, channels, st) : launch_rdif3_sg<4, false>(h, p, channels, st); break;
-        }
-        if (e3 != cudaErrorNotSupported) return e3;
     }
     switch (hopq) {
     case 1: return win ? launch_rdif_sg<1, true>(h, p, channels, st) : launch_rdif_sg<1, false>(h, p, channels, st);

@@ -36,9 +36,7 @@ struct RdifParams {
     const float* window;        // n floats (all ones for RECT)
     const float2* tw;           // W_n^m
     const float2* twm;          // W_M^m  (sub-transform twiddles)
-    const int* seg_bar;         // segment list for balanced binning
-    const int* seg_lo;
-    const int* seg_hi;
+    const int* seg_packed;      // [nseg] work list of the segment sums, longest first (see rdif_segment_sums)
     const int* bar_seg0;        // [bars+1] first segment of each bar
     const float* bar_inv;       // 1 / (hi - lo)
     const float* sg;
@@ -183,6 +181,73 @@ __device__ __forceinline__ void sg_apply(const float* cf, const float* rw, int m
     }
 }
 
+// Persistent-CTA tile cursor: tile -> (channel, tile within the channel) kept incrementally, so the tile
+// loop has no 64-bit division in front of its loads.
+struct TileCursor {
+    long long tile, tic; // global tile number; tile within its channel
+    int ch;
+    __device__ __forceinline__ void init(long long first, long long tiles_per_channel)
+    {
+        tile = first;
+        ch = (int)(first / tiles_per_channel);
+        tic = first - (long long)ch * tiles_per_channel;
+    }
+    __device__ __forceinline__ void advance(long long stride, long long tiles_per_channel)
+    {
+        tile += stride;
+        tic += stride;
+        while (tic >= tiles_per_channel) {
+            tic -= tiles_per_channel;
+            ch++;
+        }
+    }
+};
+
+// Work-list entry of the segment sums: padded first bin (13 bits) | length 1..8 (4 bits) | segment number (15 bits).
+// The list stays in bin order: neighbouring lanes then read neighbouring magnitudes, which is conflict-free
+// (sorting it by length was measured: 5 % slower from bank conflicts).
+#define FFTL_SEG_PACK(padded_lo, cnt, idx) ((padded_lo) | ((cnt) << 13) | ((idx) << 17))
+
+template <int F, int MAGS, int K> __device__ __forceinline__ void seg_steps(const float2* m0, int cnt, float* acc)
+{
+#pragma unroll
+    for (int i = 0; i < K; i++) {
+        if (i < cnt) {
+#pragma unroll
+            for (int pr = 0; pr < F / 2; pr++) {
+                const float2 a = m0[pr * MAGS + i];
+                acc[2 * pr] += a.x;
+                acc[2 * pr + 1] += a.y;
+            }
+        }
+    }
+}
+
+// Tail, first step: per-segment sums of the magnitudes of the tile's F frames.  Segments are at most 8 bins
+// long and never cross a multiple of 16, so one is at most 8 consecutive padded positions.  Every thread of
+// the calling group must take part (warp shuffles); nthreads is a multiple of 32.
+template <int F, int MAGS>
+__device__ __forceinline__ void rdif_segment_sums(const int* t_seg, const float2* mags, float* segsum, int nseg, int t, int nthreads)
+{
+    for (int base = 0; base < nseg; base += nthreads) {
+        const int sgi = base + t;
+        const int sd = sgi < nseg ? t_seg[sgi] : 0;
+        const int cnt = (sd >> 13) & 15;
+        const float2* m0 = mags + (sd & 0x1fff);
+        float acc[F];
+#pragma unroll
+        for (int f = 0; f < F; f++) acc[f] = 0.0f;
+#if defined(FFTL_SEG_FIXED8)
+        seg_steps<F, MAGS, 8>(m0, cnt, acc);
+#else
+        // the low bars are 1-2 bins wide: their warps take the short form
+        if (__reduce_max_sync(0xffffffffu, cnt) <= 2) seg_steps<F, MAGS, 2>(m0, cnt, acc);
+        else seg_steps<F, MAGS, 8>(m0, cnt, acc);
+#endif
+        if (cnt) FrameVec<F>::store(segsum + (sd >> 17) * F, acc);
+    }
+}
+
 // Row of the Savitzky-Golay matrix and first raw bar it applies to, for output bar b of B (half width w):
 // interior bars use the centre row on [b-w, b+w]; the w bars at either edge use the edge rows of the
 // polynomial fit over the first / last 2w+1 bars (scipy's mode="interp").
@@ -315,14 +380,11 @@ __global__ void __launch_bounds__(RdifShape<N, F>::THREADS, MINB) stft_bars_rdif
     float* raw = segsum + p.nseg * F;                               // [bars][F]
     float2* mags = reinterpret_cast<float2*>(reinterpret_cast<char*>(smem) + (slot_bytes > tail_bytes ? slot_bytes : tail_bytes)); // [F/2][MAGS]
     int* beat_h = reinterpret_cast<int*>(mags + (F / 2) * MAGS);    // [F][4]
-    int* t_seg = beat_h + F * 4;                                    // [nseg] padded first bin | count << 16
+    int* t_seg = beat_h + F * 4;                                    // [nseg] FFTL_SEG_PACK work list
     int* t_bar0 = reinterpret_cast<int*>(t_seg + p.nseg);           // [bars+1]
     float* t_inv = reinterpret_cast<float*>(t_bar0 + p.bars_n + 1); // [bars]
     float* t_sg = t_inv + p.bars_n;                                 // [(2w+1)^2]
-    for (int i = threadIdx.x; i < p.nseg; i += M) {
-        const int l = __ldg(p.seg_lo + i);
-        t_seg[i] = pad_index(l) | ((__ldg(p.seg_hi + i) - l) << 16);
-    }
+    for (int i = threadIdx.x; i < p.nseg; i += M) t_seg[i] = __ldg(p.seg_packed + i);
     for (int i = threadIdx.x; i <= p.bars_n; i += M) t_bar0[i] = __ldg(p.bar_seg0 + i);
     for (int i = threadIdx.x; i < p.bars_n; i += M) t_inv[i] = __ldg(p.bar_inv + i);
     for (int i = threadIdx.x; i < (2 * p.sg_half + 1) * (2 * p.sg_half + 1); i += M) t_sg[i] = p.sg ? __ldg(p.sg + i) : 0.0f;
@@ -348,9 +410,11 @@ __global__ void __launch_bounds__(RdifShape<N, F>::THREADS, MINB) stft_bars_rdif
         for (int r = 1; r < 16; r++) twc[r] = __ldg(p.twm + j * r);
     }
 
-    for (long long tile = blockIdx.x; tile < p.total_tiles; tile += gridDim.x) {
-        const int ch = (int)(tile / p.tiles_per_channel);
-        const long long f0 = p.frame0 + (tile % p.tiles_per_channel) * F; // first frame of the tile (even)
+    TileCursor cur;
+    cur.init(blockIdx.x, p.tiles_per_channel);
+    for (; cur.tile < p.total_tiles; cur.advance(gridDim.x, p.tiles_per_channel)) {
+        const int ch = cur.ch;
+        const long long f0 = p.frame0 + cur.tic * F; // first frame of the tile (even)
         const long long s0 = f0 * (long long)p.hop;                      // its first sample
         const int16_t* xp = p.pcm + (long long)ch * p.channel_stride + s0 + t;
 
@@ -463,28 +527,7 @@ __global__ void __launch_bounds__(RdifShape<N, F>::THREADS, MINB) stft_bars_rdif
         }
         __syncthreads();
         // ================= bins -> bars, SG, outputs: every item carries the tile's F frames =================
-        // segments are at most 8 bins long and never cross a multiple of 16, so a segment is 8 consecutive
-        // padded positions at most
-        for (int sgi = t; sgi < p.nseg; sgi += M) {
-            const int sd = t_seg[sgi];
-            const int cnt = sd >> 16;
-            const float2* m0 = mags + (sd & 0xffff);
-            float acc[F];
-#pragma unroll
-            for (int f = 0; f < F; f++) acc[f] = 0.0f;
-#pragma unroll
-            for (int i = 0; i < 8; i++) {
-                if (i < cnt) {
-#pragma unroll
-                    for (int pr = 0; pr < F / 2; pr++) {
-                        const float2 a = m0[pr * MAGS + i];
-                        acc[2 * pr] += a.x;
-                        acc[2 * pr + 1] += a.y;
-                    }
-                }
-            }
-            FrameVec<F>::store(segsum + sgi * F, acc);
-        }
+        rdif_segment_sums<F, MAGS>(t_seg, mags, segsum, p.nseg, t, M);
         __syncthreads();
         for (int b = t; b < B; b += M) {
             const int a = t_bar0[b], e = t_bar0[b + 1];

@@ -17,10 +17,48 @@
 // across tiles: the Hann column and the pass-A twiddles are rebuilt per tile from W_N^t, the
 // pass-C twiddles are reloaded from a 2 KB shared table.
 #pragma once
-#include "stft_rdif_ws.cuh"
-#include "stft_rdif3.cuh"
+#include "stft_rdif.cuh"
 
 namespace fftl {
+
+__device__ __forceinline__ unsigned smem_u32(const void* p) { return (unsigned)__cvta_generic_to_shared(p); }
+__device__ __forceinline__ void mbar_init(unsigned long long* bar, int count)
+{
+    asm volatile("mbarrier.init.shared::cta.b64 [%0], %1;" ::"r"(smem_u32(bar)), "r"(count));
+}
+__device__ __forceinline__ void mbar_arrive(unsigned long long* bar)
+{
+    asm volatile("mbarrier.arrive.shared::cta.b64 _, [%0];" ::"r"(smem_u32(bar)) : "memory");
+}
+__device__ __forceinline__ void mbar_wait(unsigned long long* bar, unsigned parity)
+{
+    const unsigned a = smem_u32(bar);
+    unsigned done;
+    do {
+        asm volatile(
+            "{\n"
+            ".reg .pred p;\n"
+            "mbarrier.try_wait.parity.shared::cta.b64 p, [%1], %2;\n"
+            "selp.u32 %0, 1, 0, p;\n"
+            "}\n"
+            : "=r"(done)
+            : "r"(a), "r"(parity)
+            : "memory");
+    } while (!done);
+}
+__device__ __forceinline__ void named_bar_sync(int id, int threads) { asm volatile("bar.sync %0, %1;" ::"r"(id), "r"(threads) : "memory"); }
+
+// cos / sin of q*pi/8, q = 0..15 (the Hann column of thread t is 0.5 - 0.5*cos(theta_t + q*pi/8))
+__device__ __forceinline__ constexpr float cos_pi8(int q)
+{
+    constexpr float c[16] = {1.0f, 0.92387953251128675613f, 0.70710678118654752440f, 0.38268343236508977173f,
+                             0.0f, -0.38268343236508977173f, -0.70710678118654752440f, -0.92387953251128675613f,
+                             -1.0f, -0.92387953251128675613f, -0.70710678118654752440f, -0.38268343236508977173f,
+                             0.0f, 0.38268343236508977173f, 0.70710678118654752440f, 0.92387953251128675613f};
+    return c[q];
+}
+__device__ __forceinline__ constexpr float sin_pi8(int q) { return cos_pi8((q + 12) & 15); } // sin(x) = cos(x - pi/2)
+
 
 template <int ROWS> struct RdifWs2Shape {
     static constexpr int N = 4096, M = 256, SUBG = 16, F = 4;
@@ -70,10 +108,7 @@ __global__ void __launch_bounds__(RdifWs2Shape<ROWS>::THREADS, 1) stft_bars_rdif
         }
     }
     for (int i = tid; i < 15 * 16; i += Sh::THREADS) t_twc[i] = __ldg(p.twm + (i & 15) * ((i >> 4) + 1));
-    for (int i = tid; i < p.nseg; i += Sh::THREADS) {
-        const int l = __ldg(p.seg_lo + i);
-        t_seg[i] = pad_index(l) | ((__ldg(p.seg_hi + i) - l) << 16);
-    }
+    for (int i = tid; i < p.nseg; i += Sh::THREADS) t_seg[i] = __ldg(p.seg_packed + i);
     for (int i = tid; i <= p.bars_n; i += Sh::THREADS) t_bar0[i] = __ldg(p.bar_seg0 + i);
     for (int i = tid; i < p.bars_n; i += Sh::THREADS) t_inv[i] = __ldg(p.bar_inv + i);
     for (int i = tid; i < (2 * p.sg_half + 1) * (2 * p.sg_half + 1); i += Sh::THREADS) t_sg[i] = p.sg ? __ldg(p.sg + i) : 0.0f;
@@ -93,9 +128,11 @@ __global__ void __launch_bounds__(RdifWs2Shape<ROWS>::THREADS, 1) stft_bars_rdif
 #ifdef FFTL_WS2_PROF
         long long prof_wait_ = 0, prof_t0_ = clock64();
 #endif
-        for (long long tile = 2ll * blockIdx.x + g; tile < p.total_tiles; tile += tile_stride, i++) {
-            const int ch = (int)(tile / p.tiles_per_channel);
-            const long long f0 = p.frame0 + (tile % p.tiles_per_channel) * F;
+        TileCursor cur;
+        cur.init(2ll * blockIdx.x + g, p.tiles_per_channel);
+        for (; cur.tile < p.total_tiles; cur.advance(tile_stride, p.tiles_per_channel), i++) {
+            const int ch = cur.ch;
+            const long long f0 = p.frame0 + cur.tic * F;
             const long long s0 = f0 * (long long)p.hop;
             const int16_t* xp = p.pcm + (long long)ch * p.channel_stride + s0 + t;
             // ---------------- pass A ----------------
@@ -213,13 +250,16 @@ __global__ void __launch_bounds__(RdifWs2Shape<ROWS>::THREADS, 1) stft_bars_rdif
         long long prof_wait_ = 0, prof_t0_ = clock64();
         long long ph_[6] = {0, 0, 0, 0, 0, 0};
 #endif
-        for (long long base = 2ll * blockIdx.x, i = 0; base < p.total_tiles; base += tile_stride, i++) {
-#pragma unroll 1
+        TileCursor cur2[2];
+        cur2[0].init(2ll * blockIdx.x, p.tiles_per_channel);
+        cur2[1].init(2ll * blockIdx.x + 1, p.tiles_per_channel);
+        for (long long i = 0; cur2[0].tile < p.total_tiles; i++) {
+#pragma unroll
             for (int g = 0; g < 2; g++) {
-                const long long tile = base + g;
-                if (tile >= p.total_tiles) break;
-                const int ch = (int)(tile / p.tiles_per_channel);
-                const long long f0 = p.frame0 + (tile % p.tiles_per_channel) * F;
+                TileCursor& cur = cur2[g];
+                if (cur.tile >= p.total_tiles) break;
+                const int ch = cur.ch;
+                const long long f0 = p.frame0 + cur.tic * F;
 #ifdef FFTL_WS2_PROF
                 long long c0_ = clock64();
 #endif
@@ -229,32 +269,14 @@ __global__ void __launch_bounds__(RdifWs2Shape<ROWS>::THREADS, 1) stft_bars_rdif
 #endif
 #ifdef FFTL_WS2_SKIP_TAIL
                 mbar_arrive(&mags_empty[g]);
+                cur.advance(tile_stride, p.tiles_per_channel);
                 continue;
 #endif
                 const float2* mags = mags0 + g * MAG_TILE;
 #ifdef FFTL_WS2_PROF
                 long long c1_ = clock64();
 #endif
-                for (int sgi = t; sgi < p.nseg; sgi += TT) {
-                    const int sd = t_seg[sgi];
-                    const int cnt = sd >> 16;
-                    const float2* m0 = mags + (sd & 0xffff);
-                    float acc[F];
-#pragma unroll
-                    for (int f = 0; f < F; f++) acc[f] = 0.0f;
-#pragma unroll
-                    for (int q = 0; q < 8; q++) {
-                        if (q < cnt) {
-#pragma unroll
-                            for (int pr = 0; pr < F / 2; pr++) {
-                                const float2 a = m0[pr * MAGS + q];
-                                acc[2 * pr] += a.x;
-                                acc[2 * pr + 1] += a.y;
-                            }
-                        }
-                    }
-                    FrameVec<F>::store(segsum + sgi * F, acc);
-                }
+                rdif_segment_sums<F, MAGS>(t_seg, mags, segsum, p.nseg, t, TT);
                 if (t < F && p.aux_w) { // bass bin of the tile's frames (beatDetector.c:53) before the buffer goes back
                     const long long fr = f0 + t;
                     if (fr < p.frame_end) {
@@ -298,6 +320,7 @@ __global__ void __launch_bounds__(RdifWs2Shape<ROWS>::THREADS, 1) stft_bars_rdif
                 long long c6_ = clock64();
                 ph_[0] += c2_ - c1_; ph_[1] += c3_ - c2_; ph_[2] += c4_ - c3_; ph_[3] += c5_ - c4_; ph_[4] += c6_ - c5_;
 #endif
+                cur.advance(tile_stride, p.tiles_per_channel);
             }
         }
 #ifdef FFTL_WS2_PROF

@@ -139,10 +139,10 @@ __global__ void __launch_bounds__(RdifWs2Shape<ROWS>::THREADS, 1) stft_bars_rdif
             float xr[NX];
             if (s0 + (long long)NX * M <= p.samples) {
 #pragma unroll
-                for (int r = 0; r < NX; r++) xr[r] = (float)xp[r * M];
+                for (int r = 0; r < NX; r++) xr[r] = pcm_to_float(xp + r * M);
             } else {
 #pragma unroll
-                for (int r = 0; r < NX; r++) xr[r] = (s0 + t + (long long)r * M < p.samples) ? (float)xp[r * M] : 0.0f;
+                for (int r = 0; r < NX; r++) xr[r] = (s0 + t + (long long)r * M < p.samples) ? pcm_to_float(xp + r * M) : 0.0f;
             }
             float win[16];
             if (WINDOWED) {

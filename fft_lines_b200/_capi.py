@@ -52,7 +52,7 @@ class FftlBeat(C.Structure):
 EXPORTED_FUNCTIONS = {
     "fftlines.h": [
         "fftl_config_reference", "fftl_config_extended", "fftl_config_validate", "fftl_build_bins",
-        "fftl_build_sg", "fftl_stft_create", "fftl_stft_destroy", "fftl_stft_num_frames",
+        "fftl_build_sg", "fftl_stft_create", "fftl_stft_destroy", "fftl_stft_num_frames", "fftl_stft_first_frame_needed",
         "fftl_stft_run_device", "fftl_stft_run", "fftl_stft_launch_count", "fftl_stft_timing",
         "fftl_stream_create", "fftl_stream_destroy", "fftl_stream_reset", "fftl_stream_push_device",
         "fftl_stream_push", "fftl_stream_launch_count", "fftl_stream_set_history", "fftl_stream_history_device",
@@ -101,6 +101,8 @@ def lib():
     L.fftl_stft_destroy.restype = None
     L.fftl_stft_num_frames.argtypes = [vp, C.c_int64]
     L.fftl_stft_num_frames.restype = C.c_int64
+    L.fftl_stft_first_frame_needed.argtypes = [C.c_int64, C.c_int32]
+    L.fftl_stft_first_frame_needed.restype = C.c_int64
     L.fftl_stft_run_device.argtypes = [vp, vp, C.c_int32, C.c_int64, C.c_int64, C.c_int64, C.c_int64, C.c_int64,
                                        vp, vp, vp, vp]
     L.fftl_stft_run.argtypes = [vp, vp, C.c_int32, C.c_int64, C.c_int64, C.c_int64, C.c_int64, C.c_int64, vp, vp, vp]

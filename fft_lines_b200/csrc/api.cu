@@ -269,6 +269,7 @@ struct fftl_stft {
     float* d_window;
     float2* d_tw;
     float2* d_tw256;
+    double2* d_tw256d;
     int* d_lo;
     int* d_hi;
     float* d_sg;
@@ -345,6 +346,15 @@ extern "C" int fftl_stft_create(const fftl_config* cfg, int device, fftl_stft** 
     H_TRY(cudaMemcpy(h->d_tw, tw.data(), sizeof(float2) * n, cudaMemcpyHostToDevice));
     H_TRY(cudaMalloc(&h->d_tw256, sizeof(float2) * FFTL_TEMPO_RING));
     H_TRY(cudaMemcpy(h->d_tw256, tw256.data(), sizeof(float2) * FFTL_TEMPO_RING, cudaMemcpyHostToDevice));
+    {
+        std::vector<double2> twd(FFTL_TEMPO_RING);
+        for (int m = 0; m < FFTL_TEMPO_RING; m++) {
+            double a = -2.0 * M_PI * (double)m / (double)FFTL_TEMPO_RING;
+            twd[m] = make_double2(cos(a), sin(a));
+        }
+        H_TRY(cudaMalloc(&h->d_tw256d, sizeof(double2) * FFTL_TEMPO_RING));
+        H_TRY(cudaMemcpy(h->d_tw256d, twd.data(), sizeof(double2) * FFTL_TEMPO_RING, cudaMemcpyHostToDevice));
+    }
     H_TRY(cudaMalloc(&h->d_lo, sizeof(int) * B));
     H_TRY(cudaMalloc(&h->d_hi, sizeof(int) * B));
     H_TRY(cudaMemcpy(h->d_lo, lo.data(), sizeof(int) * B, cudaMemcpyHostToDevice));
@@ -430,6 +440,7 @@ extern "C" void fftl_stft_destroy(fftl_stft* h)
     cudaFree(h->d_window);
     cudaFree(h->d_tw);
     cudaFree(h->d_tw256);
+    cudaFree(h->d_tw256d);
     cudaFree(h->d_lo);
     cudaFree(h->d_hi);
     cudaFree(h->d_sg);
@@ -459,6 +470,13 @@ extern "C" int64_t fftl_stft_num_frames(const fftl_stft* h, int64_t samples)
 {
     if (!h || samples < h->cfg.n) return 0;
     return (samples - h->cfg.n) / h->cfg.hop + 1;
+}
+
+static int64_t beat_warm_start(int64_t fb);
+extern "C" int64_t fftl_stft_first_frame_needed(int64_t frame_begin, int32_t with_beat)
+{
+    if (frame_begin < 0) frame_begin = 0;
+    return (with_beat ? beat_warm_start(frame_begin) : frame_begin) & ~(int64_t)1;
 }
 
 extern "C" int64_t fftl_stft_launch_count(const fftl_stft* h) { return h ? h->launches : 0; }
@@ -635,6 +653,7 @@ static int run_range(fftl_stft* h, const int16_t* pcm, int channels, int64_t cst
         bp.aux_bass = p.aux_bass;
         bp.out = beat + (fb - out_base);
         bp.tw256 = h->d_tw256;
+        bp.tw256d = h->d_tw256d;
         bp.aux_base = aux_base;
         bp.nf_aux = nf_aux;
         bp.frame_emit = fb;
@@ -643,14 +662,22 @@ static int run_range(fftl_stft* h, const int16_t* pcm, int channels, int64_t cst
         float dt = (float)c.hop / c.sample_rate;  // timeDelta of a batch run (fft_lines.c:265 uses wall clock)
         bp.n_times_dt = (float)c.n * dt;          // beatDetector.c:105, left-to-right in float
         bp.strict = c.strict_int;
-        const int64_t fb_even = fb & ~(int64_t)1;
-        dim3 grid((unsigned)((fe - fb_even + BEAT_FB - 1) / BEAT_FB), (unsigned)channels);
-        beat_post_kernel<<<grid, 256, 0, st>>>(bp);
+        // blocks of BEAT_FB frames aligned to absolute frame numbers
+        dim3 grid((unsigned)((fe + BEAT_FB - 1) / BEAT_FB - fb / BEAT_FB), (unsigned)channels);
+        beat_post_kernel<<<grid, BEAT_THREADS, 0, st>>>(bp);
         CUDA_TRY(cudaGetLastError());
         h->launches++;
     }
     if (evs) CUDA_TRY(cudaEventRecord(evs[2], st));
     return FFTL_OK;
+}
+
+// First frame whose (w, bass) the beat stage of a run emitting from frame fb needs: the tempo-ring transform
+// is carried forward from the start of fb's block of BEAT_FB frames, whose own state needs 256 frames of history.
+static int64_t beat_warm_start(int64_t fb)
+{
+    int64_t w = fb / BEAT_FB * BEAT_FB - FFTL_TEMPO_RING;
+    return w < 0 ? 0 : w;
 }
 
 static int check_run_args(fftl_stft* h, const void* pcm, int channels, int64_t samples, int64_t fb, int64_t fe, const void* bars)
@@ -674,8 +701,7 @@ extern "C" int fftl_stft_run_device(fftl_stft* h, const int16_t* pcm, int32_t ch
     cudaStream_t st = (cudaStream_t)cuda_stream; // NULL = CUDA's default stream, as everywhere in CUDA
     int64_t warm = fb;
     if (beat) {
-        warm = fb - FFTL_TEMPO_RING; // 255 frames of history for fb, one more for its pair partner fb^1
-        if (warm < 0) warm = 0;
+        warm = beat_warm_start(fb);
     }
     warm &= ~(int64_t)1; // frame f always shares its transform with frame f^1: results do not depend on the shard start
     int64_t nf_aux = fe - warm;
@@ -745,8 +771,7 @@ extern "C" int fftl_stft_run(fftl_stft* h, const int16_t* pcm, int32_t channels,
     const bool interleaved = (sstride != 1);
     int64_t warm = fb;
     if (beat) {
-        warm = fb - FFTL_TEMPO_RING;
-        if (warm < 0) warm = 0;
+        warm = beat_warm_start(fb);
     }
     warm &= ~(int64_t)1; // same pairing as the device path (chunks are even-sized)
     const int64_t nf_aux = fe - warm;

@@ -209,6 +209,7 @@ struct BeatParams {
     const int* aux_bass;
     fftl_beat* out;        // [channels][nf_emit]
     const float2* tw256;
+    const double2* tw256d; // the same twiddles in double (ring-transform updates)
     long long aux_base, nf_aux, frame_emit, frame_end, nf_emit;
     float n_times_dt;      // (float)N * timeDelta  (beatDetector.c:105)
     int strict;
@@ -253,44 +254,79 @@ __device__ __forceinline__ int warp_peak_pick(const int* hb, int lane)
 
 constexpr int HB_STRIDE = FFTL_BEAT_SAMPLES + 2;
 
-// Cross-frame stage for a block of 32 consecutive frames of one channel.
+// Cross-frame stage for one block of BEAT_FB consecutive frames of one channel.  Blocks are aligned to
+// ABSOLUTE frame numbers ([96 b, 96 b + 96)), so what a frame gets does not depend on where a shard starts.
 //   - bass / band-energy history of the block is staged in shared memory once;
-//   - frames f and f^1 share one complex 256-point transform of their two tempo
-//     rings (the reference feeds a real ring into a complex FFT, beatDetector.c:61-67),
-//     done by 16 lanes with warp-level syncs and untangled with shuffles;
-//   - the peak scan of a frame is split over 8 lanes (20 bins each);
+//   - the tempo ring of frame f differs from that of frame f-1 in ONE slot (f mod 256; beatDetector.c:53-59),
+//     so its 256-point transform (beatDetector.c:61-67) is updated instead of recomputed:
+//         X_f[k] = X_{f-1}[k] + (ring_new - ring_old) * W256^((f mod 256) k)
+//     The block's first state X_{fs-1} is one fp32 FFT done by 16 lanes; the updates run in double (exact to
+//     ~1e-16 per step, so the error of every frame is that of the seed: one fp32 transform, as before),
+//     one thread per bin k <= 160;
+//   - the peak scan of a frame is split over 8 lanes (20 bins each), 24 frames at a time;
 //   - AddBeatSample's 160-frame running sum is a difference of integer prefix sums.
-constexpr int BEAT_FB = 32;
-constexpr int BEAT_HBS = padded_size(FFTL_TEMPO_RING); // a frame's heightBuffer reuses half of its pair's transform buffer
-
-__global__ void __launch_bounds__(256) beat_post_kernel(const BeatParams p)
+__device__ __forceinline__ float f64_to_f32(double x)
 {
-    __shared__ int s_bass[BEAT_FB + FFTL_TEMPO_RING];          // frame fbase-256+i
-    __shared__ unsigned s_pre[BEAT_FB + FFTL_BEAT_SAMPLES + 1]; // prefix sums of w from frame fbase-159
-    __shared__ float2 s_tw[FFTL_TEMPO_RING];
-    __shared__ float2 sf[BEAT_FB / 2][padded_size(FFTL_TEMPO_RING)];
+    float r; // plain round-to-nearest: --use_fast_math would turn a C cast into a flush-to-zero sequence
+    asm("cvt.rn.f32.f64 %0, %1;" : "=f"(r) : "d"(x));
+    return r;
+}
+
+constexpr int BEAT_FB = 96;
+
+// One ring-transform update of bin k (and, when EMIT, the bin's integer height, beatDetector.c:69-75).
+// tw_i = ((f mod 256) k) mod 256 walks the twiddle table in steps of k.
+template <bool EMIT>
+__device__ __forceinline__ void beat_ring_step(const double d, const double2* twd, const int k, int& tw_i, double& xr, double& xi, int* hb, const int strict)
+{
+    const double2 w = twd[tw_i];
+    tw_i = (tw_i + k) & (FFTL_TEMPO_RING - 1);
+    xr = fma(d, w.x, xr);
+    xi = fma(d, w.y, xi);
+    if (EMIT) {
+        const float a = f64_to_f32(xr), b = f64_to_f32(xi); // what an fp32 transform would hold
+        const float mag = sqrtf(fmaf(a, a, b * b));          // finite and >= 0
+        int hv = __float2int_rz(mag);                        // saturates
+        if (strict && mag >= 2147483648.0f) hv = INT32_MIN;  // x86 cvttss2si
+        *hb = hv;
+    }
+}
+constexpr int BEAT_CH = 24;      // frames per peak-scan round (BEAT_THREADS / 8)
+constexpr int BEAT_THREADS = 192;
+constexpr int BEAT_HBROW = FFTL_BEAT_SAMPLES + 4;
+constexpr int BEAT_HBS = padded_size(FFTL_TEMPO_RING); // (streaming kernel) a frame's heightBuffer reuses half of its pair's transform buffer
+
+__global__ void __launch_bounds__(BEAT_THREADS) beat_post_kernel(const BeatParams p)
+{
+    __shared__ int s_bass[BEAT_FB + FFTL_TEMPO_RING];           // frame fs-256+i
+    __shared__ unsigned s_pre[BEAT_FB + FFTL_BEAT_SAMPLES + 1]; // prefix sums of w from frame fs-159
+    __shared__ double2 s_twd[FFTL_TEMPO_RING];
+    __shared__ float2 s_fft[padded_size(FFTL_TEMPO_RING)];
+    __shared__ int s_hb[BEAT_CH][BEAT_HBROW];
+    __shared__ double s_delta[BEAT_FB];                         // ring_new - ring_old of frame fs+i, as the floats the reference transforms
     const int tid = threadIdx.x;
     const int ch = blockIdx.y;
-    const long long fbase = (p.frame_emit & ~1ll) + (long long)blockIdx.x * BEAT_FB; // even: pairs are (f, f^1)
+    const long long fs = (p.frame_emit / BEAT_FB + (long long)blockIdx.x) * BEAT_FB;
+    const int nfr = (int)(p.frame_end - fs < BEAT_FB ? p.frame_end - fs : BEAT_FB); // frames of the block that exist
     const int* bass = p.aux_bass + (long long)ch * p.nf_aux;
     const int* wv = p.aux_w + (long long)ch * p.nf_aux;
     const long long avail_lo = p.aux_base, avail_hi = p.frame_end; // frames whose (w, bass) exist
 
     // ---- stage history
-    for (int i = tid; i < BEAT_FB + FFTL_TEMPO_RING; i += 256) {
-        long long fr = fbase - FFTL_TEMPO_RING + i;
+    for (int i = tid; i < BEAT_FB + FFTL_TEMPO_RING; i += BEAT_THREADS) {
+        long long fr = fs - FFTL_TEMPO_RING + i;
         s_bass[i] = (fr >= avail_lo && fr < avail_hi) ? __ldg(bass + (fr - p.aux_base)) : 0; // ring starts zeroed
     }
-    s_tw[tid] = __ldg(p.tw256 + tid);
-    // inclusive-exclusive prefix of w over frames fbase-159 .. fbase+31 (191 values) by warp 0:
-    // s_pre[i] = sum of the first i values, so sum(frames f-159..f) = s_pre[f-fbase+160] - s_pre[f-fbase]
+    for (int i = tid; i < FFTL_TEMPO_RING; i += BEAT_THREADS) s_twd[i] = p.tw256d[i];
+    // prefix of w over frames fs-159 .. fs+95 (255 values) by warp 0:
+    // s_pre[i] = sum of the first i values, so sum(frames f-159..f) = s_pre[f-fs+160] - s_pre[f-fs]
     if (tid < 32) {
-        constexpr int PER = 6; // 32 lanes * 6 = 192 >= 191
+        constexpr int PER = (BEAT_FB + FFTL_BEAT_SAMPLES - 1 + 31) / 32;
         unsigned loc[PER], run = 0;
 #pragma unroll
         for (int q = 0; q < PER; q++) {
             int i = tid * PER + q;
-            long long fr = fbase - (FFTL_BEAT_SAMPLES - 1) + i;
+            long long fr = fs - (FFTL_BEAT_SAMPLES - 1) + i;
             unsigned v = (i < BEAT_FB + FFTL_BEAT_SAMPLES - 1 && fr >= avail_lo && fr < avail_hi) ? (unsigned)__ldg(wv + (fr - p.aux_base)) : 0u;
             run += v;
             loc[q] = run;
@@ -311,128 +347,132 @@ __global__ void __launch_bounds__(256) beat_post_kernel(const BeatParams p)
     }
     __syncthreads();
 
-    // ---- one frame pair per 16 lanes
-    {
-        const int grp = tid >> 4, l = tid & 15;
-        const long long fa = fbase + 2 * grp; // ring slot i holds the newest frame j <= f with j % 256 == i
-        const int fa_m = (int)(fa & (FFTL_TEMPO_RING - 1));
-        const int fb_slot = (fa_m + 1) & (FFTL_TEMPO_RING - 1);
-        const int newest_b = s_bass[FFTL_TEMPO_RING + 2 * grp + 1];
-        auto sync16 = [] { __syncwarp(); };
+    if (tid < BEAT_FB) s_delta[tid] = (double)(float)s_bass[FFTL_TEMPO_RING + tid] - (double)(float)s_bass[tid]; // beatDetector.c:53-65
+    // ---- seed: transform of the ring as frame fs-1 left it; slot i holds the newest frame j <= fs-1 with j % 256 == i
+    if (tid < 16) {
+        const int l = tid;
+        const int m1 = (int)((fs - 1) & (FFTL_TEMPO_RING - 1));
+        auto sync16 = [] { __syncwarp(0xffffu); };
         float2 v[16];
 #pragma unroll
         for (int r = 0; r < 16; r++) {
-            int i = l + 16 * r;
-            int back = (fa_m - i) & (FFTL_TEMPO_RING - 1);            // frames back from fa
-            int a = s_bass[FFTL_TEMPO_RING + 2 * grp - back];           // beatDetector.c:61-65
-            int b = (i == fb_slot) ? newest_b : a;                      // frame fa+1 overwrote one slot
-            v[r] = make_float2((float)a, (float)b);
+            const int i = l + 16 * r;
+            const int back = (m1 - i) & (FFTL_TEMPO_RING - 1);                  // frames back from fs-1
+            v[r] = make_float2((float)s_bass[FFTL_TEMPO_RING - 1 - back], 0.0f); // beatDetector.c:61-65
         }
-        float2* s = sf[grp];
-        stockham_pass<256, 16, 1, 16, false>(v, s, s_tw, l, sync16);
+        stockham_pass<256, 16, 1, 16, false>(v, s_fft, p.tw256, l, sync16);
 #pragma unroll
-        for (int r = 0; r < 16; r++) v[r] = s[pad_index(l + 16 * r)];
+        for (int r = 0; r < 16; r++) v[r] = s_fft[pad_index(l + 16 * r)];
 #pragma unroll
-        for (int r = 1; r < 16; r++) v[r] = cmul(v[r], s_tw[l * r]);
+        for (int r = 1; r < 16; r++) v[r] = cmul(v[r], __ldg(p.tw256 + l * r));
         Radix<16>::run(v);
-        __syncwarp(); // every lane has read its inputs: the buffer can now hold the two heightBuffers
-        // untangle bins k = l + 16*kk <= 160 of both frames; partner 256-k sits in lane (16-l)&15
-        const int src = (16 - l) & 15;
-        int* ha = reinterpret_cast<int*>(s);
-        int* hb = ha + BEAT_HBS;
+        __syncwarp(0xffffu); // every lane has read its inputs
 #pragma unroll
-        for (int kk = 0; kk <= 10; kk++) {
-            const int rr = 4 * (kk & 3) + (kk >> 2);
-            const int kp = 15 - kk, rp = 4 * (kp & 3) + (kp >> 2);
-            float pr_ = __shfl_sync(0xffffffffu, v[rp].x, src, 16);
-            float pi_ = __shfl_sync(0xffffffffu, v[rp].y, src, 16);
-            if (l == 0) {
-                const int ks = (16 - kk) & 15, rs = 4 * (ks & 3) + (ks >> 2);
-                pr_ = v[rs].x;
-                pi_ = v[rs].y;
-            }
-            float ar = v[rr].x + pr_, ai = v[rr].y - pi_;
-            float br = v[rr].x - pr_, bi = v[rr].y + pi_;
-            const int k = l + 16 * kk;
-            if (k <= FFTL_BEAT_SAMPLES) {                               // beatDetector.c:69-75 (+ the [160] it reads OOB)
-                ha[k] = trunc_i32(0.5f * sqrtf(fmaf(ar, ar, ai * ai)), p.strict);
-                hb[k] = trunc_i32(0.5f * sqrtf(fmaf(br, br, bi * bi)), p.strict);
-            }
-        }
+        for (int rr = 0; rr < 16; rr++) s_fft[pad_index(l + 16 * Radix<16>::out_index(rr))] = v[rr];
     }
     __syncthreads();
 
-    // ---- peak scan (beatDetector.c:78-103): 8 lanes per frame, 20 bins each
-    {
-        const int fr_i = tid >> 3, sub = tid & 7;
-        const long long f = fbase + fr_i;
-        const int* h = reinterpret_cast<const int*>(sf[fr_i >> 1]) + (fr_i & 1) * BEAT_HBS;
-        const int i0 = 20 * sub;
-        unsigned bits = 0;
-        int prev = (i0 == 0) ? 0 : h[i0 - 1];
-        int cur = h[i0];
-#pragma unroll
-        for (int q = 0; q < 20; q++) {
-            int nxt = h[i0 + q + 1];
-            int dold = (i0 + q == 0) ? 0 : wrap_sub(cur, prev);
-            int dnew = wrap_sub(nxt, cur);
-            if (dold >= 0 && dnew <= 0) bits |= 1u << q;
-            prev = cur;
-            cur = nxt;
-        }
-        // peaks before this lane's range (lanes of a frame are consecutive lanes of the warp)
-        int cnt = __popc(bits), incl = cnt;
-#pragma unroll
-        for (int o = 1; o < 8; o <<= 1) {
-            int n = __shfl_up_sync(0xffffffffu, incl, o, 8);
-            if (sub >= o) incl += n;
-        }
-        int rank = incl - cnt;
-        int best_val = 0, best_idx = -1;
-        int first = bits ? (i0 + __ffs(bits) - 1) : 1 << 30;
-        unsigned bb = bits;
-        while (bb) {
-            int q = __ffs(bb) - 1;
-            bb &= bb - 1;
-            int i = i0 + q;
-            int hv = h[i];
-            if (rank < 30 && i > 30 && hv > best_val) { // only the first 30 peaks are looked at
-                best_val = hv;
-                best_idx = i;
+    const int k = tid; // bin of this thread in the update rounds
+    double xr = 0.0, xi = 0.0;
+    if (k <= FFTL_BEAT_SAMPLES) {
+        const float2 x0 = s_fft[pad_index(k)];
+        xr = (double)x0.x;
+        xi = (double)x0.y;
+    }
+    int tw_i = (int)(((fs & (FFTL_TEMPO_RING - 1)) * k) & (FFTL_TEMPO_RING - 1)); // (f mod 256) k mod 256, stepped by k per frame
+    for (int fi0 = 0; fi0 < nfr; fi0 += BEAT_CH) {
+        const bool emit_any = fs + fi0 + BEAT_CH > p.frame_emit; // block-uniform
+        if (k <= FFTL_BEAT_SAMPLES) {                           // bins 0..159 and the [160] the reference reads out of bounds
+            if (fi0 + BEAT_CH <= nfr) {
+                if (emit_any) {
+#pragma unroll 4
+                    for (int j = 0; j < BEAT_CH; j++) beat_ring_step<true>(s_delta[fi0 + j], s_twd, k, tw_i, xr, xi, &s_hb[j][k], p.strict);
+                } else {
+#pragma unroll 4
+                    for (int j = 0; j < BEAT_CH; j++) beat_ring_step<false>(s_delta[fi0 + j], s_twd, k, tw_i, xr, xi, &s_hb[j][k], p.strict);
+                }
+            } else {
+                for (int j = 0; fi0 + j < nfr; j++) {
+                    if (emit_any) beat_ring_step<true>(s_delta[fi0 + j], s_twd, k, tw_i, xr, xi, &s_hb[j][k], p.strict);
+                    else beat_ring_step<false>(s_delta[fi0 + j], s_twd, k, tw_i, xr, xi, &s_hb[j][k], p.strict);
+                }
             }
-            rank++;
         }
+        __syncthreads();
+        if (emit_any) {
+            // ---- peak scan (beatDetector.c:78-103): 8 lanes per frame, 20 bins each
+            const int fr_i = tid >> 3, sub = tid & 7;
+            const int fi = fi0 + fr_i;
+            const long long f = fs + fi;
+            const int* h = s_hb[fr_i];
+            const int i0 = 20 * sub;
+            unsigned bits = 0;
+            int prev = (i0 == 0) ? 0 : h[i0 - 1];
+            int cur = h[i0];
 #pragma unroll
-        for (int o = 4; o > 0; o >>= 1) {
-            int ov = __shfl_xor_sync(0xffffffffu, best_val, o, 8);
-            int oi = __shfl_xor_sync(0xffffffffu, best_idx, o, 8);
-            int of = __shfl_xor_sync(0xffffffffu, first, o, 8);
-            bool take = (oi >= 0) && (best_idx < 0 || ov > best_val || (ov == best_val && oi < best_idx));
-            if (take) {
-                best_val = ov;
-                best_idx = oi;
+            for (int q = 0; q < 20; q++) {
+                int nxt = h[i0 + q + 1];
+                int dold = (i0 + q == 0) ? 0 : wrap_sub(cur, prev);
+                int dnew = wrap_sub(nxt, cur);
+                if (dold >= 0 && dnew <= 0) bits |= 1u << q;
+                prev = cur;
+                cur = nxt;
             }
-            first = of < first ? of : first;
+            // peaks before this lane's range (lanes of a frame are consecutive lanes of the warp)
+            int cnt = __popc(bits), incl = cnt;
+#pragma unroll
+            for (int o = 1; o < 8; o <<= 1) {
+                int n = __shfl_up_sync(0xffffffffu, incl, o, 8);
+                if (sub >= o) incl += n;
+            }
+            int rank = incl - cnt;
+            int best_val = 0, best_idx = -1;
+            int first = bits ? (i0 + __ffs(bits) - 1) : 1 << 30;
+            unsigned bb = bits;
+            while (bb) {
+                int q = __ffs(bb) - 1;
+                bb &= bb - 1;
+                int i = i0 + q;
+                int hv = h[i];
+                if (rank < 30 && i > 30 && hv > best_val) { // only the first 30 peaks are looked at
+                    best_val = hv;
+                    best_idx = i;
+                }
+                rank++;
+            }
+#pragma unroll
+            for (int o = 4; o > 0; o >>= 1) {
+                int ov = __shfl_xor_sync(0xffffffffu, best_val, o, 8);
+                int oi = __shfl_xor_sync(0xffffffffu, best_idx, o, 8);
+                int of = __shfl_xor_sync(0xffffffffu, first, o, 8);
+                bool take = (oi >= 0) && (best_idx < 0 || ov > best_val || (ov == best_val && oi < best_idx));
+                if (take) {
+                    best_val = ov;
+                    best_idx = oi;
+                }
+                first = of < first ? of : first;
+            }
+            if (sub == 0 && f >= p.frame_emit && f < p.frame_end) {
+                int peak = best_idx >= 0 ? best_idx : (first < (1 << 30) ? first : 0);
+                // AddBeatSample: sum of the last 160 band energies (beatDetector.c:32-41)
+                int part = (int)(s_pre[fi + FFTL_BEAT_SAMPLES] - s_pre[fi]);
+                int wcur = (int)(s_pre[fi + FFTL_BEAT_SAMPLES] - s_pre[fi + FFTL_BEAT_SAMPLES - 1]);
+                int thr = part / FFTL_BEAT_SAMPLES;                 // beatDetector.c:41
+                float qv = __fdiv_rn((float)wcur, (float)thr);      // IEEE: x/0 = inf, 0/0 = NaN
+                int bv = trunc_i32(__fmul_rn(qv, 128.0f), 1);       // beatDetector.c:43 (always x86 semantics)
+                fftl_beat rec;
+                rec.w = wcur;
+                rec.thr = thr;
+                rec.beat_value = bv;
+                rec.flag = (thr > 0 && wcur > thr) ? 1 : 0;
+                rec.bass = s_bass[FFTL_TEMPO_RING + fi];
+                rec.peak_index = peak;
+                rec.movement_per_sec = __fmul_rn(p.n_times_dt, (float)peak); // beatDetector.c:105
+                rec.reserved = 0;
+                p.out[(long long)ch * p.nf_emit + (f - p.frame_emit)] = rec;
+            }
         }
-        if (sub == 0 && f >= p.frame_emit && f < p.frame_end) {
-            int peak = best_idx >= 0 ? best_idx : (first < (1 << 30) ? first : 0);
-            // AddBeatSample: sum of the last 160 band energies (beatDetector.c:32-41)
-            int part = (int)(s_pre[fr_i + FFTL_BEAT_SAMPLES] - s_pre[fr_i]);
-            int wcur = (int)(s_pre[fr_i + FFTL_BEAT_SAMPLES] - s_pre[fr_i + FFTL_BEAT_SAMPLES - 1]);
-            int thr = part / FFTL_BEAT_SAMPLES;                 // beatDetector.c:41
-            float qv = __fdiv_rn((float)wcur, (float)thr);      // IEEE: x/0 = inf, 0/0 = NaN
-            int bv = trunc_i32(__fmul_rn(qv, 128.0f), 1);       // beatDetector.c:43 (always x86 semantics)
-            fftl_beat rec;
-            rec.w = wcur;
-            rec.thr = thr;
-            rec.beat_value = bv;
-            rec.flag = (thr > 0 && wcur > thr) ? 1 : 0;
-            rec.bass = s_bass[FFTL_TEMPO_RING + fr_i];
-            rec.peak_index = peak;
-            rec.movement_per_sec = __fmul_rn(p.n_times_dt, (float)peak); // beatDetector.c:105
-            rec.reserved = 0;
-            p.out[(long long)ch * p.nf_emit + (f - p.frame_emit)] = rec;
-        }
+        __syncthreads(); // the next round overwrites s_hb
     }
 }
 

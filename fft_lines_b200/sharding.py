@@ -1,8 +1,8 @@
 """Frame-range sharding of one STFT job across GPUs.
 
-Frames are independent up to the bar heights, and the beat stages need only the
-previous 255 frames' two integers, which ``fftl_stft_run*`` recomputes itself
-for any ``frame_begin``.  So a shard is just a ``[begin, end)`` frame range: no
+Frames are independent up to the bar heights, and the beat stages need only two
+integers per frame of a bounded history (at most 96 + 256 frames back), which
+``fftl_stft_run*`` recomputes itself for any ``frame_begin``.  So a shard is just a ``[begin, end)`` frame range: no
 data-path collective, only an optional final gather of the outputs.
 """
 
@@ -17,12 +17,25 @@ def shard_frames(total_frames, world_size, rank):
     return begin, end
 
 
-def sample_span(frame_begin, frame_end, n, hop, warmup_frames=255):
+BEAT_BLOCK = 96   # frames per block of the beat stage (csrc/kernels.cuh BEAT_FB)
+TEMPO_RING = 256  # beatDetector.c:53-59
+
+
+def first_frame_needed(frame_begin, with_beat=True):
+    """Mirror of ``fftl_stft_first_frame_needed``: the first frame whose samples a run from
+    ``frame_begin`` reads (the tempo-ring state is carried forward from the start of the
+    frame's 96-frame block, which itself needs 256 frames of history)."""
+    fb = max(0, int(frame_begin))
+    if with_beat:
+        fb = max(0, fb // BEAT_BLOCK * BEAT_BLOCK - TEMPO_RING)
+    return fb & ~1
+
+
+def sample_span(frame_begin, frame_end, n, hop, with_beat=True):
     """Samples a shard must hold: its frames plus the beat warm-up halo before it."""
     if frame_end <= frame_begin:
         return 0, 0
-    first = max(0, frame_begin - warmup_frames)
-    return first * hop, (frame_end - 1) * hop + n
+    return first_frame_needed(frame_begin, with_beat) * hop, (frame_end - 1) * hop + n
 
 
 def gather_frames(local, total_frames, group=None, dst=None):

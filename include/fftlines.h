@@ -107,6 +107,11 @@ int     fftl_stft_create(const fftl_config* cfg, int device, fftl_stft** out);
 void    fftl_stft_destroy(fftl_stft* h);
 /* F = floor((samples - n)/hop) + 1, or 0. */
 int64_t fftl_stft_num_frames(const fftl_stft* h, int64_t samples_per_channel);
+/* First frame a run over [frame_begin, frame_end) reads samples of: frame_begin itself (rounded down to even)
+ * without beat output; with beat output the band-energy / bass history it recomputes in front of the range
+ * (the start of frame_begin's 96-frame block minus the 256-entry tempo ring, beatDetector.c:53-67).
+ * A shard must hold samples [first*hop, (frame_end-1)*hop + n) of every channel. */
+int64_t fftl_stft_first_frame_needed(int64_t frame_begin, int32_t with_beat);
 
 /* PCM addressing: sample s of channel c is pcm[c*channel_stride + s*sample_stride]
  * (planar: channel_stride = samples, sample_stride = 1; interleaved: 1, channels).

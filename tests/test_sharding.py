@@ -27,7 +27,8 @@ def test_shard_frames_partition(lib):
 def test_sample_span_includes_beat_halo(lib):
     sh = lib.sharding
     assert sh.sample_span(0, 10, 4096, 512) == (0, 9 * 512 + 4096)
-    assert sh.sample_span(1000, 2000, 4096, 512) == ((1000 - 255) * 512, 1999 * 512 + 4096)
+    assert sh.sample_span(1000, 2000, 4096, 512) == ((960 - 256) * 512, 1999 * 512 + 4096)
+    assert sh.sample_span(1001, 2000, 4096, 512, with_beat=False) == (1000 * 512, 1999 * 512 + 4096)
     assert sh.sample_span(100, 200, 4096, 512) == (0, 199 * 512 + 4096)
     assert sh.sample_span(5, 5, 4096, 512) == (0, 0)
 
@@ -73,3 +74,13 @@ def test_two_rank_gloo_shards_equal_single_run(oracle, tmp_path):
     assert (bars == full["bars"]).all()
     for k in ("w", "thr", "beat_value", "flag", "bass", "peak_index", "movement_per_sec"):
         assert (beat[k] == full["beat"][k]).all(), k
+
+
+def test_first_frame_needed_matches_library(lib):
+    """The Python mirror agrees with fftl_stft_first_frame_needed (host arithmetic only: runs without a GPU)."""
+    from fft_lines_b200 import _capi, sharding as sh
+    L = _capi.lib()
+    for fb in (0, 1, 95, 96, 97, 255, 256, 257, 351, 352, 353, 1000, 1001, 10 ** 9 + 7):
+        for wb in (0, 1):
+            assert L.fftl_stft_first_frame_needed(fb, wb) == sh.first_frame_needed(fb, bool(wb)), (fb, wb)
+    assert sh.first_frame_needed(400) == 384 - 256 and sh.first_frame_needed(100) == 0

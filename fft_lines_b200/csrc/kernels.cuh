@@ -274,23 +274,57 @@ __device__ __forceinline__ float f64_to_f32(double x)
 
 constexpr int BEAT_FB = 96;
 
-// One ring-transform update of bin k (and, when EMIT, the bin's integer height, beatDetector.c:69-75).
-// tw_i = ((f mod 256) k) mod 256 walks the twiddle table in steps of k.
-template <bool EMIT>
-__device__ __forceinline__ void beat_ring_step(const double d, const double2* twd, const int k, int& tw_i, double& xr, double& xi, int* hb, const int strict)
+// NF consecutive ring-transform updates of bin k (and, when EMIT, the bin's integer heights,
+// beatDetector.c:69-75).  tw_i = ((f mod 256) k) mod 256 walks the twiddle table in steps of k.
+// Written stage by stage over the NF frames so that the loads, the conversions and the square roots of
+// different frames overlap: only the two fma chains are serial.
+template <bool EMIT, int NF>
+__device__ __forceinline__ void beat_ring_steps(const double* delta, const double2* twd, const int k, int& tw_i, double& xr, double& xi, int* hb,
+                                                const int hb_stride, const int strict)
 {
-    const double2 w = twd[tw_i];
-    tw_i = (tw_i + k) & (FFTL_TEMPO_RING - 1);
-    xr = fma(d, w.x, xr);
-    xi = fma(d, w.y, xi);
+    double d[NF];
+    double2 w[NF];
+#pragma unroll
+    for (int i = 0; i < NF; i++) {
+        d[i] = delta[i];
+        w[i] = twd[tw_i];
+        tw_i = (tw_i + k) & (FFTL_TEMPO_RING - 1);
+    }
+    double ar[NF], ai[NF];
+#pragma unroll
+    for (int i = 0; i < NF; i++) {
+        xr = fma(d[i], w[i].x, xr);
+        xi = fma(d[i], w[i].y, xi);
+        ar[i] = xr;
+        ai[i] = xi;
+    }
     if (EMIT) {
-        const float a = f64_to_f32(xr), b = f64_to_f32(xi); // what an fp32 transform would hold
-        const float mag = sqrtf(fmaf(a, a, b * b));          // finite and >= 0
-        int hv = __float2int_rz(mag);                        // saturates
-        if (strict && mag >= 2147483648.0f) hv = INT32_MIN;  // x86 cvttss2si
-        *hb = hv;
+        // |X|^2 in double, one conversion, one square root; the float -> int truncation is done on the FP32
+        // pipe: below 2^23, mag + 2^23 rounded toward zero has trunc(mag) in its mantissa
+        float mag[NF];
+        bool big = false;
+#pragma unroll
+        for (int i = 0; i < NF; i++) {
+            mag[i] = sqrtf(f64_to_f32(fma(ar[i], ar[i], ai[i] * ai[i]))); // finite and >= 0
+            big |= mag[i] >= 8388608.0f;
+        }
+        int hv[NF];
+#pragma unroll
+        for (int i = 0; i < NF; i++) hv[i] = __float_as_int(__fadd_rz(mag[i], 8388608.0f)) - 0x4B000000;
+        if (__any_sync(__activemask(), big)) { // bin 0 of a loud ring, hardly any other
+#pragma unroll
+            for (int i = 0; i < NF; i++) {
+                if (mag[i] >= 8388608.0f) {
+                    hv[i] = __float2int_rz(mag[i]);                           // saturates
+                    if (strict && mag[i] >= 2147483648.0f) hv[i] = INT32_MIN; // x86 cvttss2si
+                }
+            }
+        }
+#pragma unroll
+        for (int i = 0; i < NF; i++) hb[i * hb_stride] = hv[i];
     }
 }
+
 constexpr int BEAT_CH = 24;      // frames per peak-scan round (BEAT_THREADS / 8)
 constexpr int BEAT_THREADS = 192;
 constexpr int BEAT_HBROW = FFTL_BEAT_SAMPLES + 4;
@@ -385,16 +419,16 @@ __global__ void __launch_bounds__(BEAT_THREADS) beat_post_kernel(const BeatParam
         if (k <= FFTL_BEAT_SAMPLES) {                           // bins 0..159 and the [160] the reference reads out of bounds
             if (fi0 + BEAT_CH <= nfr) {
                 if (emit_any) {
-#pragma unroll 4
-                    for (int j = 0; j < BEAT_CH; j++) beat_ring_step<true>(s_delta[fi0 + j], s_twd, k, tw_i, xr, xi, &s_hb[j][k], p.strict);
+#pragma unroll 1
+                    for (int j = 0; j < BEAT_CH; j += 4) beat_ring_steps<true, 4>(s_delta + fi0 + j, s_twd, k, tw_i, xr, xi, &s_hb[j][k], BEAT_HBROW, p.strict);
                 } else {
-#pragma unroll 4
-                    for (int j = 0; j < BEAT_CH; j++) beat_ring_step<false>(s_delta[fi0 + j], s_twd, k, tw_i, xr, xi, &s_hb[j][k], p.strict);
+#pragma unroll 1
+                    for (int j = 0; j < BEAT_CH; j += 4) beat_ring_steps<false, 4>(s_delta + fi0 + j, s_twd, k, tw_i, xr, xi, &s_hb[j][k], BEAT_HBROW, p.strict);
                 }
             } else {
                 for (int j = 0; fi0 + j < nfr; j++) {
-                    if (emit_any) beat_ring_step<true>(s_delta[fi0 + j], s_twd, k, tw_i, xr, xi, &s_hb[j][k], p.strict);
-                    else beat_ring_step<false>(s_delta[fi0 + j], s_twd, k, tw_i, xr, xi, &s_hb[j][k], p.strict);
+                    if (emit_any) beat_ring_steps<true, 1>(s_delta + fi0 + j, s_twd, k, tw_i, xr, xi, &s_hb[j][k], BEAT_HBROW, p.strict);
+                    else beat_ring_steps<false, 1>(s_delta + fi0 + j, s_twd, k, tw_i, xr, xi, &s_hb[j][k], BEAT_HBROW, p.strict);
                 }
             }
         }

@@ -1038,7 +1038,10 @@ extern "C" int fftl_stream_push_device(fftl_stream* s, const int16_t* fresh, int
         fresh += count - c.n;
         count = c.n;
     }
-    stream_slide_kernel<<<s->streams, 256, 0, st>>>(s->d_window, fresh, c.n, count, stride, s->move_mode == FFTL_MOVE_REFERENCE);
+    if (s->move_mode != FFTL_MOVE_REFERENCE && (count & 7) == 0 && (c.n & 7) == 0 && (stride & 7) == 0 && ((uintptr_t)fresh & 15) == 0)
+        stream_slide_vec_kernel<<<s->streams, 256, 0, st>>>(s->d_window, fresh, c.n, count, stride);
+    else
+        stream_slide_kernel<<<s->streams, 256, 0, st>>>(s->d_window, fresh, c.n, count, stride, s->move_mode == FFTL_MOVE_REFERENCE);
     CUDA_TRY(cudaGetLastError());
     // one frame per stream: channels = streams, samples = n
     int rc = run_range(h, s->d_window, s->streams, c.n, 1, c.n, 1, 0, 0, 1, 0, 1, 0, 1, bars, bars_i32, true, nullptr, st, nullptr, true);
@@ -1055,6 +1058,7 @@ extern "C" int fftl_stream_push_device(fftl_stream* s, const int16_t* fresh, int
     bp.streams = s->streams;
     bp.n_times_dt = (float)c.n * dt;
     bp.strict = c.strict_int;
+    bp.finish = s->d_hist ? 0 : 1; // the history push, when enabled, is the last kernel
     stream_beat_kernel<<<(s->streams + 31) / 32, 256, 0, st>>>(bp);
     CUDA_TRY(cudaGetLastError());
     if (s->d_hist) {
@@ -1065,9 +1069,7 @@ extern "C" int fftl_stream_push_device(fftl_stream* s, const int16_t* fresh, int
         CUDA_TRY(cudaGetLastError());
         s->launches++;
     }
-    stream_tick_kernel<<<1, 1, 0, st>>>(s->d_state);
-    CUDA_TRY(cudaGetLastError());
-    s->launches += 4;
+    s->launches += 3;
     return FFTL_OK;
 }
 

@@ -63,7 +63,7 @@ struct StftParams {
 };
 
 template <int N> struct StftShape {
-    static constexpr int VPT = (N >= 16384) ? 32 : 16;
+    static constexpr int VPT = (N >= 16384) ? 32 : 16; // (16 -> 1024 threads at 64 registers was measured at N = 16384: 25 % slower)
     static constexpr int G = N / VPT;                       // threads per frame pair
     static constexpr int PAIRS = (G >= 256) ? 1 : (256 / G > 8 ? 8 : 256 / G);
     static constexpr int THREADS = G * PAIRS;
@@ -335,6 +335,7 @@ __global__ void __launch_bounds__(BEAT_THREADS) beat_post_kernel(const BeatParam
     __shared__ int s_bass[BEAT_FB + FFTL_TEMPO_RING];           // frame fs-256+i
     __shared__ unsigned s_pre[BEAT_FB + FFTL_BEAT_SAMPLES + 1]; // prefix sums of w from frame fs-159
     __shared__ double2 s_twd[FFTL_TEMPO_RING];
+    __shared__ float2 s_tw[FFTL_TEMPO_RING];
     __shared__ float2 s_fft[padded_size(FFTL_TEMPO_RING)];
     __shared__ int s_hb[BEAT_CH][BEAT_HBROW];
     __shared__ double s_delta[BEAT_FB];                         // ring_new - ring_old of frame fs+i, as the floats the reference transforms
@@ -351,7 +352,10 @@ __global__ void __launch_bounds__(BEAT_THREADS) beat_post_kernel(const BeatParam
         long long fr = fs - FFTL_TEMPO_RING + i;
         s_bass[i] = (fr >= avail_lo && fr < avail_hi) ? __ldg(bass + (fr - p.aux_base)) : 0; // ring starts zeroed
     }
-    for (int i = tid; i < FFTL_TEMPO_RING; i += BEAT_THREADS) s_twd[i] = p.tw256d[i];
+    for (int i = tid; i < FFTL_TEMPO_RING; i += BEAT_THREADS) {
+        s_twd[i] = p.tw256d[i];
+        s_tw[i] = __ldg(p.tw256 + i);
+    }
     // prefix of w over frames fs-159 .. fs+95 (255 values) by warp 0:
     // s_pre[i] = sum of the first i values, so sum(frames f-159..f) = s_pre[f-fs+160] - s_pre[f-fs]
     if (tid < 32) {
@@ -394,11 +398,11 @@ __global__ void __launch_bounds__(BEAT_THREADS) beat_post_kernel(const BeatParam
             const int back = (m1 - i) & (FFTL_TEMPO_RING - 1);                  // frames back from fs-1
             v[r] = make_float2((float)s_bass[FFTL_TEMPO_RING - 1 - back], 0.0f); // beatDetector.c:61-65
         }
-        stockham_pass<256, 16, 1, 16, false>(v, s_fft, p.tw256, l, sync16);
+        stockham_pass<256, 16, 1, 16, false>(v, s_fft, s_tw, l, sync16);
 #pragma unroll
         for (int r = 0; r < 16; r++) v[r] = s_fft[pad_index(l + 16 * r)];
 #pragma unroll
-        for (int r = 1; r < 16; r++) v[r] = cmul(v[r], __ldg(p.tw256 + l * r));
+        for (int r = 1; r < 16; r++) v[r] = cmul(v[r], s_tw[l * r]);
         Radix<16>::run(v);
         __syncwarp(0xffffu); // every lane has read its inputs
 #pragma unroll

@@ -8,8 +8,8 @@
 //                         off-by-one, wasapi_audio.cpp:394)
 //   stft_bars_kernel<N>   one frame per stream (kernels.cuh)
 //   stream_beat_kernel    AddBeatSample + BassBeatDetector on per-stream rings
-// All three take their positions from a device-resident tick counter, so the
-// triple can be captured once in a CUDA graph and replayed every tick.
+// All three take their positions from a device-resident tick counter (advanced by the last CTA
+// of the push's last kernel), so the triple can be captured once in a CUDA graph and replayed every tick.
 #pragma once
 #include "kernels.cuh"
 
@@ -17,7 +17,45 @@ namespace fftl {
 
 struct StreamState {
     long long tick;      // number of completed pushes
+    unsigned done;       // CTAs of the push's last kernel that have finished (stream_finish)
 };
+
+// Called by every CTA of the LAST kernel of a push when it is done: the CTA that finishes last advances the
+// tick.  Every CTA has read the tick before it gets here, so no separate one-thread launch is needed.
+__device__ __forceinline__ void stream_finish(StreamState* st)
+{
+    __syncthreads();
+    if (threadIdx.x == 0) {
+        __threadfence();
+        if (atomicAdd(&st->done, 1u) == gridDim.x - 1) {
+            st->done = 0;
+            st->tick++;
+        }
+    }
+}
+
+// Vector form of stream_slide_kernel for shift, keep and the fresh rows all multiples of 8 samples (16 bytes).
+__global__ void __launch_bounds__(256) stream_slide_vec_kernel(int16_t* __restrict__ window, const int16_t* __restrict__ fresh, int n, int count,
+                                                               long long fresh_stride)
+{
+    const int s = blockIdx.x;
+    uint4* w = reinterpret_cast<uint4*>(window + (long long)s * n);
+    const uint4* f = reinterpret_cast<const uint4*>(fresh + (long long)s * fresh_stride);
+    const int nv = n >> 3, shiftv = count >> 3, keepv = nv - shiftv;
+    constexpr int PER = 8; // 256 threads * 8 vectors * 8 samples = 16384 samples max
+    uint4 v[PER];
+#pragma unroll
+    for (int i = 0; i < PER; i++) {
+        const int k = threadIdx.x + i * 256;
+        if (k < nv) v[i] = (k < keepv) ? w[k + shiftv] : __ldg(f + (k - keepv));
+    }
+    __syncthreads();
+#pragma unroll
+    for (int i = 0; i < PER; i++) {
+        const int k = threadIdx.x + i * 256;
+        if (k < nv) w[k] = v[i];
+    }
+}
 
 // window[s][0..n) <- shift by `count` (or count-1 in reference mode), append new[s][0..count)
 // One CTA per stream; the window is staged through registers so the shift is safe in place.
@@ -56,6 +94,7 @@ struct StreamBeatParams {
     int streams;
     float n_times_dt;       // (float)N * timeDelta of this tick
     int strict;
+    int finish;             // this is the push's last kernel: advance the tick when done
 };
 
 // 32 streams per CTA: streams 2g, 2g+1 share one complex 256-point transform of their tempo rings.
@@ -194,11 +233,12 @@ __global__ void __launch_bounds__(256) stream_beat_kernel(const StreamBeatParams
             p.out[s] = rec;
         }
     }
+    if (p.finish) stream_finish(p.state);
 }
 
 // history ring: hist[s][tick % depth][b] = bars[s][b]
 __global__ void __launch_bounds__(256) stream_history_push_kernel(float* __restrict__ hist, const float* __restrict__ bars,
-                                                                  const StreamState* state, int streams, int depth, int nbars)
+                                                                  StreamState* state, int streams, int depth, int nbars)
 {
     const int slot = (int)(state->tick % depth);
     const long long total = (long long)streams * nbars;
@@ -207,6 +247,7 @@ __global__ void __launch_bounds__(256) stream_history_push_kernel(float* __restr
         const int b = (int)(i - s * nbars);
         hist[(s * depth + slot) * nbars + b] = bars[i];
     }
+    stream_finish(state); // always the push's last kernel
 }
 
 // out[s][k][b], k = 0 oldest ... depth-1 newest; `tick` pushes have been made so far
@@ -239,6 +280,5 @@ __global__ void __launch_bounds__(256) stream_waveform_kernel(const int16_t* __r
 }
 
 // advances the tick once per push, after every block of stream_beat_kernel has read it
-__global__ void stream_tick_kernel(StreamState* st) { st->tick++; }
 
 } // namespace fftl

@@ -184,6 +184,18 @@ def main():
         raise SystemExit("bench.py: no CUDA device; libfftlines_cuda has no CPU fallback")
     torch.cuda.set_device(local_rank)
     dev = torch.device("cuda", local_rank)
+    numa = None
+    if world > 1 and not os.environ.get("FFTL_NO_AFFINITY"):
+        # Run this rank on the CPUs next to its GPU before any pinned buffer exists: the e2e leg streams
+        # >1 GB per step between host and device, and first-touch then puts the pinned pages on the GPU's
+        # own NUMA node instead of wherever torchrun happened to start the process.
+        try:
+            import pynvml
+            pynvml.nvmlInit()
+            pynvml.nvmlDeviceSetCpuAffinity(pynvml.nvmlDeviceGetHandleByIndex(local_rank))
+            numa = "rank bound to its GPU's CPU set (nvmlDeviceSetCpuAffinity): %d cpus" % len(os.sched_getaffinity(0))
+        except Exception as e:  # affinity is an optimisation, never a requirement
+            numa = "not bound: %s" % e
     if world > 1:
         dist.init_process_group("nccl", device_id=dev)
 
@@ -262,6 +274,8 @@ def main():
                "d2h_bytes_per_step": int(CHANNELS * nf * BARS * 4 + CHANNELS * nf * F.BEAT_DTYPE.itemsize),
                "steps": e2e_steps, "ms_per_step": 1e3 * dt / e2e_steps,
                "api": "fftl_stft_run (host int16 PCM -> host float bars + beat records, pinned buffers)"}
+        if numa:
+            e2e["host_affinity"] = numa
         h_pcm.free(); h_bars.free(); h_beat.free()
 
     # ---------------- CPU baseline beside it (rank 0, N=1 only) ----------------

@@ -140,3 +140,57 @@ def test_device_path_matches_host_path(oracle, lib):
     b = lib.BatchedSpectrum.beat_to_numpy(beat)
     for k in ("w", "thr", "beat_value", "flag", "bass", "peak_index", "movement_per_sec"):
         assert (b[k] == host["beat"][k]).all(), k
+
+
+BEAT_FIELDS = ("w", "thr", "beat_value", "flag", "bass", "peak_index", "movement_per_sec")
+
+
+def test_shards_around_beat_blocks_equal_full_run(oracle, lib):
+    """The beat stage carries the tempo-ring transform forward inside absolute blocks of 96 frames
+    (beatDetector.c:53-67): a shard starting anywhere relative to a block must reproduce the full run bit for bit,
+    both through the fast path (4096/512) and the generic one (2048/300)."""
+    for cfg, samples in ((lib.extended_config(4096, 512, 200), 4096 + 699 * 512), (lib.extended_config(2048, 300, 100), 2048 + 699 * 300)):
+        pcm = oracle.synth_pcm(2, samples)
+        with lib.BatchedSpectrum(cfg) as sp:
+            full = sp.run(pcm)
+            for fb, fe in ((1, 700), (95, 400), (96, 400), (97, 193), (191, 700), (192, 289), (353, 354), (640, 700)):
+                part = sp.run(pcm, fb, fe)
+                assert (part["bars"] == full["bars"][:, fb:fe]).all(), (cfg.n, fb, fe)
+                assert (part["bars_i32"] == full["bars_i32"][:, fb:fe]).all(), (cfg.n, fb, fe)
+                for k in BEAT_FIELDS:
+                    assert (part["beat"][k] == full["beat"][k][:, fb:fe]).all(), (cfg.n, k, fb, fe)
+
+
+def test_host_chunks_straddle_beat_blocks(oracle, lib):
+    """fftl_stft_run moves a long job in frame-range chunks (about 21 000 frames each here) whose boundaries fall
+    inside the beat stage's 96-frame blocks: the chunked host path must equal one device-resident call."""
+    import torch
+    cfg = lib.extended_config(4096, 512, 200)
+    frames = 48000
+    d = torch.empty((2, 4096 + (frames - 1) * 512), dtype=torch.int16, device="cuda")
+    lib.synth_pcm_device(d)
+    torch.cuda.synchronize()
+    pcm = d.cpu().numpy()
+    with lib.BatchedSpectrum(cfg) as sp:
+        host = sp.run(pcm, 1000, frames, want_i32=False)
+        bars, _, beat = sp.alloc_device_outputs(2, frames - 1000, "cuda", want_i32=False)
+        sp.run_device(d, bars, None, beat, 1000, frames)
+        torch.cuda.synchronize()
+    assert (bars.cpu().numpy() == host["bars"]).all()
+    b = lib.BatchedSpectrum.beat_to_numpy(beat)
+    for k in BEAT_FIELDS:
+        assert (b[k] == host["beat"][k]).all(), k
+    # and the integer chain of a stretch that crosses a chunk boundary is what the oracle replays
+    ocfg = oracle.Config()
+    import ctypes as C
+    C.memmove(C.byref(ocfg), C.byref(cfg), C.sizeof(ocfg))
+    full_w = np.zeros(frames, np.int32)
+    full_bass = np.zeros(frames, np.int32)
+    with lib.BatchedSpectrum(cfg) as sp:
+        head = sp.run(pcm, 0, 1000, want_i32=False)
+    full_w[:1000], full_bass[:1000] = head["beat"]["w"][0], head["beat"]["bass"][0]
+    full_w[1000:], full_bass[1000:] = host["beat"]["w"][0], host["beat"]["bass"][0]
+    rep = oracle.beat_replay(ocfg, full_w[:24000], full_bass[:24000])
+    for k in ("thr", "beat_value", "flag"):
+        assert (rep[k][1000:] == host["beat"][k][0, :23000]).all(), k
+    assert (rep["peak_index"][1000:] == host["beat"]["peak_index"][0, :23000]).mean() > 0.97

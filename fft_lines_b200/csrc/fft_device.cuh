@@ -103,6 +103,71 @@ template <> struct Radix<16> {
     __host__ __device__ __forceinline__ static constexpr int out_index(int r) { return 4 * (r & 3) + (r >> 2); }
 };
 
+// ---- radix-16 with the multiplies folded into the butterflies (fast path only) ----------------------
+// a + w*b with both products as fused multiply-adds (4 FFMA), and the matching difference as 2a - (a + w*b)
+// (2 FFMA): a twiddled radix-2 costs 6 instructions instead of 8.
+__device__ __forceinline__ float2 cfma(float2 a, float2 w, float2 b) // a + w*b
+{
+    return make_float2(fmaf(w.x, b.x, fmaf(-w.y, b.y, a.x)), fmaf(w.x, b.y, fmaf(w.y, b.x, a.y)));
+}
+__device__ __forceinline__ float2 ctwice_minus(float2 a, float2 t) { return make_float2(fmaf(2.0f, a.x, -t.x), fmaf(2.0f, a.y, -t.y)); }
+
+// forward 4-point DFT of (a0, w1*b1, w2*b2, w3*b3), natural order; a0 comes in already multiplied
+__device__ __forceinline__ void dft4_tw(float2& a0, float2& b1, float2& b2, float2& b3, float2 w1, float2 w2, float2 w3)
+{
+    const float2 t0 = cfma(a0, w2, b2), t1 = ctwice_minus(a0, t0);   // a0 +- w2 b2
+    const float2 a1 = cmul(b1, w1);
+    const float2 t2 = cfma(a1, w3, b3), d = ctwice_minus(a1, t2);    // a1 +- w3 b3
+    a0 = cadd(t0, t2);
+    b2 = csub(t0, t2);
+    b1 = make_float2(t1.x + d.y, t1.y - d.x);                        // t1 - i d
+    b3 = make_float2(t1.x - d.y, t1.y + d.x);                        // t1 + i d
+}
+
+// Radix<16>::run with (TW) every input but v[0] first multiplied by tw[r]; same output order.
+template <bool TW> __device__ __forceinline__ void radix16_fused(float2* v, const float2* tw)
+{
+    constexpr float2 W1 = {FFTL_COS_PI_8, -FFTL_SIN_PI_8}, W3 = {FFTL_SIN_PI_8, -FFTL_COS_PI_8};
+    constexpr float2 W9 = {-FFTL_COS_PI_8, FFTL_SIN_PI_8};
+    if (TW) {
+        dft4_tw(v[0], v[4], v[8], v[12], tw[4], tw[8], tw[12]);
+#pragma unroll
+        for (int n1 = 1; n1 < 4; n1++) {
+            v[n1] = cmul(v[n1], tw[n1]);
+            dft4_tw(v[n1], v[n1 + 4], v[n1 + 8], v[n1 + 12], tw[n1 + 4], tw[n1 + 8], tw[n1 + 12]);
+        }
+    } else {
+#pragma unroll
+        for (int n1 = 0; n1 < 4; n1++) dft4(v[n1], v[n1 + 4], v[n1 + 8], v[n1 + 12]);
+    }
+    // second stage: v[n1 + 4*k2] *= W16^(n1*k2), then 4-point DFTs over n1
+    dft4(v[0], v[1], v[2], v[3]);
+    {   // k2 = 1: (1, W16^1, W16^2, W16^3)
+        const float2 b2 = cmul_w8_1(v[6]);
+        const float2 t0 = cadd(v[4], b2), t1 = csub(v[4], b2);
+        const float2 a1 = cmul_w16_1(v[5]);
+        const float2 t2 = cfma(a1, W3, v[7]), d = ctwice_minus(a1, t2);
+        v[4] = cadd(t0, t2);
+        v[6] = csub(t0, t2);
+        v[5] = make_float2(t1.x + d.y, t1.y - d.x);
+        v[7] = make_float2(t1.x - d.y, t1.y + d.x);
+    }
+    v[9] = cmul_w8_1(v[9]);    // k2 = 2: (1, W16^2, W16^4, W16^6)
+    v[10] = cmul_mi(v[10]);
+    v[11] = cmul_w8_3(v[11]);
+    dft4(v[8], v[9], v[10], v[11]);
+    {   // k2 = 3: (1, W16^3, W16^6, W16^9)
+        const float2 b2 = cmul_w8_3(v[14]);
+        const float2 t0 = cadd(v[12], b2), t1 = csub(v[12], b2);
+        const float2 a1 = cmul_w16_3(v[13]);
+        const float2 t2 = cfma(a1, W9, v[15]), d = ctwice_minus(a1, t2);
+        v[12] = cadd(t0, t2);
+        v[14] = csub(t0, t2);
+        v[13] = make_float2(t1.x + d.y, t1.y - d.x);
+        v[15] = make_float2(t1.x - d.y, t1.y + d.x);
+    }
+}
+
 __host__ __device__ __forceinline__ constexpr int pad_index(int i) { return i + (i >> 4); }
 __host__ __device__ __forceinline__ constexpr int padded_size(int n) { return n + (n >> 4); }
 

@@ -85,11 +85,13 @@ __device__ __forceinline__ void real_dft16(const float* x, const float* w, float
     yi[6] = b2 - m;
     // odd outputs: c_q = d_q - i d_{q+4}; g_q = c_q W16^q; complex DFT-4 of g gives
     // Y[1], Y[5], conj(Y[7]), conj(Y[3])
-    float2 g0 = make_float2(d[0], -d[4]);
-    float2 g1 = cmul_w16_1(make_float2(d[1], -d[5]));
-    float2 g2 = cmul_w8_1(make_float2(d[2], -d[6]));
-    float2 g3 = cmul_w16_3(make_float2(d[3], -d[7]));
-    dft4(g0, g1, g2, g3);
+    // (the 4-point DFT of g with W16^3 c3 folded into its butterflies: q1 +- W16^3 c3 = u2, 2 q1 - u2)
+    const float2 c0 = make_float2(d[0], -d[4]), q2 = cmul_w8_1(make_float2(d[2], -d[6]));
+    const float2 u0 = cadd(c0, q2), u1 = csub(c0, q2);
+    const float2 q1 = cmul_w16_1(make_float2(d[1], -d[5]));
+    const float2 u2 = cfma(q1, make_float2(FFTL_SIN_PI_8, -FFTL_COS_PI_8), make_float2(d[3], -d[7])), dd = ctwice_minus(q1, u2);
+    const float2 g0 = cadd(u0, u2), g2 = csub(u0, u2);
+    const float2 g1 = make_float2(u1.x + dd.y, u1.y - dd.x), g3 = make_float2(u1.x - dd.y, u1.y + dd.x);
     yr[1] = g0.x; yi[1] = g0.y;
     yr[5] = g1.x; yi[5] = g1.y;
     yr[7] = g2.x; yi[7] = -g2.y;
@@ -476,13 +478,22 @@ __global__ void __launch_bounds__(RdifShape<N, F>::THREADS, MINB) stft_bars_rdif
         auto pass_bc = [&](const int pr) {
             float2* s = slots + (pr * 16 + hw) * SLOT;
             float2 v[16];
-            stockham_pass<M, 16, 1, SUBG, true>(v, s, p.twm, j, wsync);
-            // second sub-pass; results stay in registers
+            // first sub-pass (no twiddles): radix 16 over t = j + 16 r, result X1[16 j + k] back into the slot
 #pragma unroll
             for (int r = 0; r < 16; r++) v[r] = s[pad_index(j + r * (M / 16))];
+            radix16_fused<false>(v, nullptr);
+            wsync();
 #pragma unroll
-            for (int r = 1; r < 16; r++) v[r] = cmul(v[r], RESIDENT ? twc[r] : ldg_pinned(p.twm + j * r));
-            Radix<16>::run(v);
+            for (int rr = 0; rr < 16; rr++) s[pad_index(16 * j + Radix<16>::out_index(rr))] = v[rr];
+            wsync();
+            // second sub-pass; the W_M^(j r) multiplies are folded into its first butterflies, results stay in registers
+#pragma unroll
+            for (int r = 0; r < 16; r++) v[r] = s[pad_index(j + r * (M / 16))];
+            if (!RESIDENT) {
+#pragma unroll
+                for (int r = 1; r < 16; r++) twc[r] = ldg_pinned(p.twm + j * r);
+            }
+            radix16_fused<true>(v, twc);
             // v[rr] = Z[m], m = j + 16*kk, kk = out_index(rr)
             float2* mg2 = mags + pr * MAGS;
             if (hw >= 2) {

@@ -481,6 +481,22 @@ extern "C" int64_t fftl_stft_first_frame_needed(int64_t frame_begin, int32_t wit
 
 extern "C" int64_t fftl_stft_launch_count(const fftl_stft* h) { return h ? h->launches : 0; }
 
+// Tile bookkeeping of the fast path: tiles of F frames per channel and the tile ranges the kernel may treat
+// without edge handling (TileCursor).  False when a channel has too many tiles for the 32-bit cursor.
+static bool rdif_set_tiles(RdifParams& p, int channels, int F, int hopq)
+{
+    p.tiles_per_channel = (p.frame_end - p.frame0 + F - 1) / F;
+    p.total_tiles = p.tiles_per_channel * channels;
+    if (p.tiles_per_channel >= (1ll << 30)) return false;
+    const long long span = (16 + (long long)hopq * (F - 1)) * 256;              // samples a tile reads per channel
+    const long long q = p.samples - span - p.frame0 * (long long)p.hop;
+    long long full = q < 0 ? 0 : q / ((long long)F * p.hop) + 1;                // tiles whose samples all exist
+    p.tic_full = (int)(full > p.tiles_per_channel ? p.tiles_per_channel : full);
+    p.tic_emit_lo = (int)((p.frame_emit - p.frame0 + F - 1) / F);               // first tile that starts at or after frame_emit
+    p.tic_emit_hi = (int)((p.frame_end - p.frame0) / F);                        // tiles that end at or before frame_end
+    return true;
+}
+
 // Fast path (stft_rdif.cuh).  Returns cudaErrorNotSupported when the configuration is not covered.
 template <int F, int HOPQ, bool WIN, int SGW, int ROWS>
 static cudaError_t launch_rdif(const fftl_stft* h, RdifParams p, int channels, cudaStream_t st)
@@ -489,8 +505,7 @@ static cudaError_t launch_rdif(const fftl_stft* h, RdifParams p, int channels, c
     using Sh = RdifShape<4096, F>;
     size_t smem = Sh::smem_bytes(p.bars_n, p.nseg, p.sg_half, ROWS);
     if ((smem + 1024) * MINB > 228 * 1024) return cudaErrorNotSupported;
-    p.tiles_per_channel = (p.frame_end - p.frame0 + F - 1) / F;
-    p.total_tiles = p.tiles_per_channel * channels;
+    if (!rdif_set_tiles(p, channels, F, HOPQ)) return cudaErrorNotSupported;
     if (p.total_tiles <= 0) return cudaSuccess;
     auto kern = stft_bars_rdif_kernel<4096, F, HOPQ, WIN, true, MINB, SGW, ROWS>;
     cudaError_t e = cudaFuncSetAttribute(kern, cudaFuncAttributeMaxDynamicSharedMemorySize, (int)smem);
@@ -517,8 +532,7 @@ static cudaError_t launch_rdif_ws2(const fftl_stft* h, RdifParams p, int channel
     using Sh = RdifWs2Shape<ROWS>;
     size_t smem = Sh::smem_bytes(p.bars_n, p.nseg, p.sg_half);
     if (smem > 227 * 1024) return cudaErrorNotSupported;
-    p.tiles_per_channel = (p.frame_end - p.frame0 + Sh::F - 1) / Sh::F;
-    p.total_tiles = p.tiles_per_channel * channels;
+    if (!rdif_set_tiles(p, channels, Sh::F, HOPQ)) return cudaErrorNotSupported;
     if (p.total_tiles <= 0) return cudaSuccess;
     auto kern = stft_bars_rdif_ws2_kernel<HOPQ, WIN, SGW, ROWS>;
     cudaError_t e = cudaFuncSetAttribute(kern, cudaFuncAttributeMaxDynamicSharedMemorySize, (int)smem);

@@ -33,6 +33,8 @@ struct RdifParams {
     long long nf_emit, nf_aux, aux_base;
     long long tiles_per_channel;
     long long total_tiles;
+    int tic_full;               // tiles with tic < tic_full have all their samples inside the channel
+    int tic_emit_lo, tic_emit_hi; // tiles with tic in [lo, hi) emit all their frames
     const float* window;        // n floats (all ones for RECT)
     const float2* tw;           // W_n^m
     const float2* twm;          // W_M^m  (sub-transform twiddles)
@@ -196,26 +198,40 @@ __device__ __forceinline__ void sg_apply(const float* cf, const float* rw, int m
     }
 }
 
-// Persistent-CTA tile cursor: tile -> (channel, tile within the channel) kept incrementally, so the tile
-// loop has no 64-bit division in front of its loads.
+// Persistent-CTA tile cursor: tile -> (channel, tile within the channel), the tile's first sample and its
+// place in the outputs are all carried from tile to tile, so the tile loop has neither a 64-bit division nor
+// 64-bit multiplies in front of its loads.  tiles_per_channel < 2^31 (checked by the launcher).
 struct TileCursor {
-    long long tile, tic; // global tile number; tile within its channel
-    int ch;
-    __device__ __forceinline__ void init(long long first, long long tiles_per_channel)
+    int left;           // tiles this CTA still has to do
+    int tic, ch;        // tile within its channel; channel
+    const int16_t* xp;  // first sample of the tile in its channel
+    long long o0;       // element offset of (ch, first frame of the tile, bar 0) in the outputs; meaningless for warm-up tiles
+    long long dx, dox;  // per-advance steps of xp and o0
+    __device__ __forceinline__ void init(const RdifParams& p, long long first, long long stride, int F)
     {
-        tile = first;
-        ch = (int)(first / tiles_per_channel);
-        tic = first - (long long)ch * tiles_per_channel;
+        left = first < p.total_tiles ? (int)((p.total_tiles - first + stride - 1) / stride) : 0;
+        ch = (int)(first / p.tiles_per_channel);
+        tic = (int)(first - (long long)ch * p.tiles_per_channel);
+        const long long f0 = p.frame0 + (long long)tic * F;
+        xp = p.pcm + (long long)ch * p.channel_stride + f0 * p.hop;
+        o0 = ((long long)ch * p.nf_emit + (f0 - p.frame_emit)) * p.bars_n;
+        dx = stride * F * p.hop;
+        dox = stride * F * p.bars_n;
     }
-    __device__ __forceinline__ void advance(long long stride, long long tiles_per_channel)
+    __device__ __forceinline__ void advance(const RdifParams& p, int stride, int F)
     {
-        tile += stride;
+        left--;
         tic += stride;
-        while (tic >= tiles_per_channel) {
-            tic -= tiles_per_channel;
+        xp += dx;
+        o0 += dox;
+        while (tic >= (int)p.tiles_per_channel) { // next channel (more than once only when the grid outnumbers a channel's tiles)
+            tic -= (int)p.tiles_per_channel;
             ch++;
+            xp += p.channel_stride - p.tiles_per_channel * F * p.hop;
+            o0 += (p.nf_emit - p.tiles_per_channel * F) * p.bars_n;
         }
     }
+    __device__ __forceinline__ long long first_frame(const RdifParams& p, int F) const { return p.frame0 + (long long)tic * F; }
 };
 
 // Work-list entry of the segment sums: padded first bin (13 bits) | length 1..8 (4 bits) | segment number (15 bits).
@@ -277,14 +293,12 @@ __device__ __forceinline__ void sg_row(int b, int B, int w, int& row, int& base)
 // that the fast and the careful branch round alike (a frame can sit in an edge tile of one shard and in
 // an interior tile of the full run).
 template <int F, int SGW>
-__device__ __forceinline__ void rdif_emit_bars(const RdifParams& p, const float* raw, const float* t_sg, int t, int nthreads, int ch, long long f0)
+__device__ __forceinline__ void rdif_emit_bars(const RdifParams& p, const float* raw, const float* t_sg, int t, int nthreads, bool interior, long long o0,
+                                               long long f0)
 {
     const int B = p.bars_n;
     const int w = SGW >= 0 ? SGW : p.sg_half, m = 2 * w + 1;
-    // frames of this tile that are emitted: [e_lo, e_hi)
-    const long long dlo = p.frame_emit - f0, dhi = p.frame_end - f0;
-    const long long o0 = ((long long)ch * p.nf_emit + (f0 - p.frame_emit)) * B;
-    if (dlo <= 0 && dhi >= F && p.bars_i32 == nullptr) {
+    if (interior && p.bars_i32 == nullptr) {
         // every frame of the tile is emitted, float heights only: nothing to predicate
 #pragma unroll 1
         for (int b = t; b < B; b += nthreads) {
@@ -301,6 +315,8 @@ __device__ __forceinline__ void rdif_emit_bars(const RdifParams& p, const float*
         }
         return;
     }
+    // frames of this tile that are emitted: [e_lo, e_hi)
+    const long long dlo = p.frame_emit - f0, dhi = p.frame_end - f0;
     const int e_lo = dlo > 0 ? (dlo < F ? (int)dlo : F) : 0;
     const int e_hi = dhi < F ? (dhi > 0 ? (int)dhi : 0) : F;
     const int cadd = (int)p.circle_add;
@@ -426,19 +442,17 @@ __global__ void __launch_bounds__(RdifShape<N, F>::THREADS, MINB) stft_bars_rdif
     }
 
     TileCursor cur;
-    cur.init(blockIdx.x, p.tiles_per_channel);
-    for (; cur.tile < p.total_tiles; cur.advance(gridDim.x, p.tiles_per_channel)) {
-        const int ch = cur.ch;
-        const long long f0 = p.frame0 + cur.tic * F; // first frame of the tile (even)
-        const long long s0 = f0 * (long long)p.hop;                      // its first sample
-        const int16_t* xp = p.pcm + (long long)ch * p.channel_stride + s0 + t;
+    cur.init(p, blockIdx.x, gridDim.x, F);
+    for (; cur.left > 0; cur.advance(p, gridDim.x, F)) {
+        const int16_t* xp = cur.xp + t;
 
         // ================= pass A =================
         float xr[NX];
-        if (s0 + (long long)NX * M <= p.samples) {
+        if (cur.tic < p.tic_full) {
 #pragma unroll
             for (int r = 0; r < NX; r++) xr[r] = pcm_to_float(xp + r * M);
         } else {
+            const long long s0 = cur.first_frame(p, F) * (long long)p.hop; // the tile's first sample
 #pragma unroll
             for (int r = 0; r < NX; r++) xr[r] = (s0 + t + (long long)r * M < p.samples) ? pcm_to_float(xp + r * M) : 0.0f;
         }
@@ -579,8 +593,8 @@ __global__ void __launch_bounds__(RdifShape<N, F>::THREADS, MINB) stft_bars_rdif
         }
         __syncthreads();
         // band energy / bass first (16 lanes of warp 0; the magnitudes are still in place), then the heights
-        rdif_emit_beat<F, SGW>(p, raw, t_sg, mags, MAGS, t, ch, f0);
-        rdif_emit_bars<F, SGW>(p, raw, t_sg, t, M, ch, f0);
+        if (t < 4 * F) rdif_emit_beat<F, SGW>(p, raw, t_sg, mags, MAGS, t, cur.ch, cur.first_frame(p, F));
+        rdif_emit_bars<F, SGW>(p, raw, t_sg, t, M, cur.tic >= p.tic_emit_lo && cur.tic < p.tic_emit_hi, cur.o0, cur.first_frame(p, F));
         // No barrier here: the next tile's pass A starts at once; the barrier that protects the aliased
         // buffers is the one inside (late_alias) or in front of (otherwise) its pass A.
     }

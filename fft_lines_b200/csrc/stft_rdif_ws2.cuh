@@ -129,10 +129,10 @@ __global__ void __launch_bounds__(RdifWs2Shape<ROWS>::THREADS, 1) stft_bars_rdif
         long long prof_wait_ = 0, prof_t0_ = clock64();
 #endif
         TileCursor cur;
-        cur.init(2ll * blockIdx.x + g, p.tiles_per_channel);
-        for (; cur.tile < p.total_tiles; cur.advance(tile_stride, p.tiles_per_channel), i++) {
+        cur.init(p, 2ll * blockIdx.x + g, tile_stride, F);
+        for (; cur.left > 0; cur.advance(p, (int)tile_stride, F), i++) {
             const int ch = cur.ch;
-            const long long f0 = p.frame0 + cur.tic * F;
+            const long long f0 = cur.first_frame(p, F);
             const long long s0 = f0 * (long long)p.hop;
             const int16_t* xp = p.pcm + (long long)ch * p.channel_stride + s0 + t;
             // ---------------- pass A ----------------
@@ -251,15 +251,15 @@ __global__ void __launch_bounds__(RdifWs2Shape<ROWS>::THREADS, 1) stft_bars_rdif
         long long ph_[6] = {0, 0, 0, 0, 0, 0};
 #endif
         TileCursor cur2[2];
-        cur2[0].init(2ll * blockIdx.x, p.tiles_per_channel);
-        cur2[1].init(2ll * blockIdx.x + 1, p.tiles_per_channel);
-        for (long long i = 0; cur2[0].tile < p.total_tiles; i++) {
+        cur2[0].init(p, 2ll * blockIdx.x, tile_stride, F);
+        cur2[1].init(p, 2ll * blockIdx.x + 1, tile_stride, F);
+        for (long long i = 0; cur2[0].left > 0; i++) {
 #pragma unroll
             for (int g = 0; g < 2; g++) {
                 TileCursor& cur = cur2[g];
-                if (cur.tile >= p.total_tiles) break;
+                if (cur.left <= 0) break;
                 const int ch = cur.ch;
-                const long long f0 = p.frame0 + cur.tic * F;
+                const long long f0 = cur.first_frame(p, F);
 #ifdef FFTL_WS2_PROF
                 long long c0_ = clock64();
 #endif
@@ -269,7 +269,7 @@ __global__ void __launch_bounds__(RdifWs2Shape<ROWS>::THREADS, 1) stft_bars_rdif
 #endif
 #ifdef FFTL_WS2_SKIP_TAIL
                 mbar_arrive(&mags_empty[g]);
-                cur.advance(tile_stride, p.tiles_per_channel);
+                cur.advance(p, (int)tile_stride, F);
                 continue;
 #endif
                 const float2* mags = mags0 + g * MAG_TILE;
@@ -315,12 +315,12 @@ __global__ void __launch_bounds__(RdifWs2Shape<ROWS>::THREADS, 1) stft_bars_rdif
                 long long c5_ = clock64();
 #endif
                 rdif_emit_beat<F, SGW>(p, raw, t_sg, nullptr, MAGS, t, ch, f0);
-                rdif_emit_bars<F, SGW>(p, raw, t_sg, t, TT, ch, f0);
+                rdif_emit_bars<F, SGW>(p, raw, t_sg, t, TT, cur.tic >= p.tic_emit_lo && cur.tic < p.tic_emit_hi, cur.o0, f0);
 #ifdef FFTL_WS2_PROF
                 long long c6_ = clock64();
                 ph_[0] += c2_ - c1_; ph_[1] += c3_ - c2_; ph_[2] += c4_ - c3_; ph_[3] += c5_ - c4_; ph_[4] += c6_ - c5_;
 #endif
-                cur.advance(tile_stride, p.tiles_per_channel);
+                cur.advance(p, (int)tile_stride, F);
             }
         }
 #ifdef FFTL_WS2_PROF

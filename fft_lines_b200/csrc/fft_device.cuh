@@ -127,8 +127,7 @@ __device__ __forceinline__ void dft4_tw(float2& a0, float2& b1, float2& b2, floa
 // Radix<16>::run with (TW) every input but v[0] first multiplied by tw[r]; same output order.
 template <bool TW> __device__ __forceinline__ void radix16_fused(float2* v, const float2* tw)
 {
-    constexpr float2 W1 = {FFTL_COS_PI_8, -FFTL_SIN_PI_8}, W3 = {FFTL_SIN_PI_8, -FFTL_COS_PI_8};
-    constexpr float2 W9 = {-FFTL_COS_PI_8, FFTL_SIN_PI_8};
+    constexpr float2 W3 = {FFTL_SIN_PI_8, -FFTL_COS_PI_8}, W9 = {-FFTL_COS_PI_8, FFTL_SIN_PI_8}; // W16^3, W16^9
     if (TW) {
         dft4_tw(v[0], v[4], v[8], v[12], tw[4], tw[8], tw[12]);
 #pragma unroll

@@ -488,7 +488,7 @@ static bool rdif_set_tiles(RdifParams& p, int channels, int F, int hopq)
     p.tiles_per_channel = (p.frame_end - p.frame0 + F - 1) / F;
     p.total_tiles = p.tiles_per_channel * channels;
     if (p.tiles_per_channel >= (1ll << 30)) return false;
-    const long long span = (16 + (long long)hopq * (F - 1)) * 256;              // samples a tile reads per channel
+    const long long span = hopq ? (16 + (long long)hopq * (F - 1)) * 256 : (long long)(F - 1) * p.hop + 4096; // samples a tile reads per channel
     const long long q = p.samples - span - p.frame0 * (long long)p.hop;
     long long full = q < 0 ? 0 : q / ((long long)F * p.hop) + 1;                // tiles whose samples all exist
     p.tic_full = (int)(full > p.tiles_per_channel ? p.tiles_per_channel : full);
@@ -560,9 +560,11 @@ static cudaError_t launch_rdif_sg(const fftl_stft* h, const RdifParams& p, int c
 static cudaError_t try_rdif(const fftl_stft* h, const StftParams& q, int channels, long long samples, cudaStream_t st)
 {
     const fftl_config& c = h->cfg;
-    if (c.n != 4096 || q.sample_stride != 1 || (c.hop % 256) != 0) return cudaErrorNotSupported;
-    const int hopq = c.hop / 256;
-    if (hopq != 1 && hopq != 2 && hopq != 4) return cudaErrorNotSupported;
+    if (c.n != 4096 || q.sample_stride != 1) return cudaErrorNotSupported;
+    // hop = 256, 512 or 1024: the frames of a tile share their samples in registers; any other hop: the
+    // variant in which every frame loads its own (hopq = 0)
+    int hopq = (c.hop % 256) == 0 ? c.hop / 256 : 0;
+    if (hopq != 1 && hopq != 2 && hopq != 4) hopq = 0;
     if (getenv("FFTL_DISABLE_RDIF") || !h->seg_packable) return cudaErrorNotSupported;
     RdifParams p;
     memset(&p, 0, sizeof(p));
@@ -606,6 +608,7 @@ static cudaError_t try_rdif(const fftl_stft* h, const StftParams& q, int channel
         if (ew != cudaErrorNotSupported) return ew;
     }
     switch (hopq) {
+    case 0: return win ? launch_rdif_rows<0, true, -1>(h, p, channels, st) : launch_rdif_rows<0, false, -1>(h, p, channels, st);
     case 1: return win ? launch_rdif_sg<1, true>(h, p, channels, st) : launch_rdif_sg<1, false>(h, p, channels, st);
     case 2: return win ? launch_rdif_sg<2, true>(h, p, channels, st) : launch_rdif_sg<2, false>(h, p, channels, st);
     default: return win ? launch_rdif_sg<4, true>(h, p, channels, st) : launch_rdif_sg<4, false>(h, p, channels, st);

@@ -397,7 +397,9 @@ __global__ void __launch_bounds__(RdifShape<N, F>::THREADS, MINB) stft_bars_rdif
     constexpr int MAGS = Sh::mag_stride(ROWS);
     static_assert(N == 4096, "this instantiation covers N = 4096 (M = 256, two radix-16 sub-passes)");
     static_assert(F == 2 || F == 4, "frames are packed in pairs; the tail moves F floats as one vector");
-    constexpr int NX = 16 + HOPQ * (F - 1);          // samples per column per tile
+    // HOPQ > 0: hop = HOPQ*M, the tile's frames share their samples (NX per column per tile).
+    // HOPQ = 0: any hop; every frame loads its own 16 samples per column, one frame pair (32) at a time.
+    constexpr int NX = HOPQ ? 16 + HOPQ * (F - 1) : 32;
 
     extern __shared__ float2 smem[];
     float2* slots = smem;                                           // [F/2][16][SLOT]
@@ -448,7 +450,25 @@ __global__ void __launch_bounds__(RdifShape<N, F>::THREADS, MINB) stft_bars_rdif
 
         // ================= pass A =================
         float xr[NX];
-        if (cur.tic < p.tic_full) {
+        const bool all_samples = cur.tic < p.tic_full; // every sample the tile reads exists
+        auto load_pair = [&](const int pr) {           // HOPQ = 0: samples of frames 2pr, 2pr+1 of the tile
+#pragma unroll
+            for (int h = 0; h < 2; h++) {
+                const long long off = (long long)(2 * pr + h) * p.hop;
+                const int16_t* xf = xp + off;
+                if (all_samples) {
+#pragma unroll
+                    for (int q = 0; q < 16; q++) xr[16 * h + q] = pcm_to_float(xf + q * M);
+                } else {
+                    const long long s0 = cur.first_frame(p, F) * (long long)p.hop + off + t;
+#pragma unroll
+                    for (int q = 0; q < 16; q++) xr[16 * h + q] = (s0 + (long long)q * M < p.samples) ? pcm_to_float(xf + q * M) : 0.0f;
+                }
+            }
+        };
+        if (HOPQ == 0) {
+            load_pair(0);
+        } else if (all_samples) {
 #pragma unroll
             for (int r = 0; r < NX; r++) xr[r] = pcm_to_float(xp + r * M);
         } else {
@@ -475,7 +495,7 @@ __global__ void __launch_bounds__(RdifShape<N, F>::THREADS, MINB) stft_bars_rdif
             for (int h = 0; h < 2; h++) {
                 const int f = 2 * pr + h;
                 float yr[9], yi[9];
-                real_dft16<WINDOWED>(xr + HOPQ * f, win, yr, yi);
+                real_dft16<WINDOWED>(HOPQ ? xr + HOPQ * f : xr + 16 * h, win, yr, yi);
                 y0[h] = yr[0];
                 y8[h] = yr[8];
                 // slots 2*k0 + h (k0 = 1..7): frame h of the pair, residue k0
@@ -563,6 +583,7 @@ __global__ void __launch_bounds__(RdifShape<N, F>::THREADS, MINB) stft_bars_rdif
         // aliases onto the last pair's slots (late_alias).  (Running B/C(0) right behind A(1), with the second
         // barrier after it, was measured: 1.3 % slower with the tail's seven magnitude rows, equal without.)
         pass_a(0);
+        if (HOPQ == 0 && F == 4) load_pair(1); // in flight across the barrier
         __syncthreads();
         if (F == 4) {
             pass_a(1);

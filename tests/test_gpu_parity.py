@@ -194,3 +194,29 @@ def test_host_chunks_straddle_beat_blocks(oracle, lib):
     for k in ("thr", "beat_value", "flag"):
         assert (rep[k][1000:] == host["beat"][k][0, :23000]).all(), k
     assert (rep["peak_index"][1000:] == host["beat"]["peak_index"][0, :23000]).mean() > 0.97
+
+
+@pytest.mark.parametrize("hop", [441, 480, 768, 1000, 2048, 4096, 5000])
+def test_fast_path_any_hop(oracle, lib, hop):
+    """N = 4096 with a hop that is not 256/512/1024 runs the fast kernel's own-samples variant: against the
+    oracle (parity bar), against the generic kernel (tolerance) and shard == full run (bit exact)."""
+    import os
+    cfg = lib.extended_config(4096, hop, 200)
+    pcm = oracle.synth_pcm(2, 4096 + 130 * hop + 17)  # 131 frames, ragged tail
+    got, _ = _check(oracle, lib, cfg, pcm)
+    with lib.BatchedSpectrum(cfg) as sp:
+        before = sp.launch_count
+        part = sp.run(pcm, 37, 120)
+        os.environ["FFTL_DISABLE_RDIF"] = "1"
+        try:
+            gen = sp.run(pcm)
+        finally:
+            del os.environ["FFTL_DISABLE_RDIF"]
+    assert (part["bars"] == got["bars"][:, 37:120]).all()
+    for k in BEAT_FIELDS:
+        assert (part["beat"][k] == got["beat"][k][:, 37:120]).all(), k
+    fmax = np.abs(gen["bars"]).max(axis=-1, keepdims=True)
+    assert (np.abs(gen["bars"] - got["bars"]) <= 2e-6 * fmax).all()
+    # reference mode (no window, linear bins) through the same variant
+    rcfg = lib.reference_config(4096, hop, 100)
+    _check(oracle, lib, rcfg, pcm[:, :4096 + 40 * hop])

@@ -560,16 +560,17 @@ static cudaError_t launch_rdif_sg(const fftl_stft* h, const RdifParams& p, int c
 static cudaError_t try_rdif(const fftl_stft* h, const StftParams& q, int channels, long long samples, cudaStream_t st)
 {
     const fftl_config& c = h->cfg;
-    if (c.n != 4096 || q.sample_stride != 1) return cudaErrorNotSupported;
-    // hop = 256, 512 or 1024: the frames of a tile share their samples in registers; any other hop: the
-    // variant in which every frame loads its own (hopq = 0)
+    if (c.n != 4096) return cudaErrorNotSupported;
+    // hop = 256, 512 or 1024 on planar PCM: the frames of a tile share their samples in registers; any other
+    // hop, or interleaved PCM: the variant in which every frame loads its own (hopq = 0)
     int hopq = (c.hop % 256) == 0 ? c.hop / 256 : 0;
-    if (hopq != 1 && hopq != 2 && hopq != 4) hopq = 0;
+    if ((hopq != 1 && hopq != 2 && hopq != 4) || q.sample_stride != 1) hopq = 0;
     if (getenv("FFTL_DISABLE_RDIF") || !h->seg_packable) return cudaErrorNotSupported;
     RdifParams p;
     memset(&p, 0, sizeof(p));
     p.pcm = q.pcm;
     p.channel_stride = q.channel_stride;
+    p.sample_stride = q.sample_stride;
     p.samples = samples;
     p.frame0 = q.frame0;
     p.frame_emit = q.frame_emit;

@@ -27,7 +27,8 @@ namespace fftl {
 
 struct RdifParams {
     const int16_t* pcm;
-    long long channel_stride;   // sample_stride is 1 on this path
+    long long channel_stride;
+    long long sample_stride;    // 1 (planar) except in the HOPQ = 0 variant, which also takes interleaved PCM
     long long samples;          // samples per channel (loads beyond it read as 0)
     long long frame0, frame_emit, frame_end, frames_total;
     long long nf_emit, nf_aux, aux_base;
@@ -213,9 +214,9 @@ struct TileCursor {
         ch = (int)(first / p.tiles_per_channel);
         tic = (int)(first - (long long)ch * p.tiles_per_channel);
         const long long f0 = p.frame0 + (long long)tic * F;
-        xp = p.pcm + (long long)ch * p.channel_stride + f0 * p.hop;
+        xp = p.pcm + (long long)ch * p.channel_stride + f0 * p.hop * p.sample_stride;
         o0 = ((long long)ch * p.nf_emit + (f0 - p.frame_emit)) * p.bars_n;
-        dx = stride * F * p.hop;
+        dx = stride * F * p.hop * p.sample_stride;
         dox = stride * F * p.bars_n;
     }
     __device__ __forceinline__ void advance(const RdifParams& p, int stride, int F)
@@ -227,7 +228,7 @@ struct TileCursor {
         while (tic >= (int)p.tiles_per_channel) { // next channel (more than once only when the grid outnumbers a channel's tiles)
             tic -= (int)p.tiles_per_channel;
             ch++;
-            xp += p.channel_stride - p.tiles_per_channel * F * p.hop;
+            xp += p.channel_stride - p.tiles_per_channel * F * p.hop * p.sample_stride;
             o0 += (p.nf_emit - p.tiles_per_channel * F) * p.bars_n;
         }
     }
@@ -446,7 +447,7 @@ __global__ void __launch_bounds__(RdifShape<N, F>::THREADS, MINB) stft_bars_rdif
     TileCursor cur;
     cur.init(p, blockIdx.x, gridDim.x, F);
     for (; cur.left > 0; cur.advance(p, gridDim.x, F)) {
-        const int16_t* xp = cur.xp + t;
+        const int16_t* xp = cur.xp + (HOPQ ? (long long)t : t * p.sample_stride);
 
         // ================= pass A =================
         float xr[NX];
@@ -455,14 +456,15 @@ __global__ void __launch_bounds__(RdifShape<N, F>::THREADS, MINB) stft_bars_rdif
 #pragma unroll
             for (int h = 0; h < 2; h++) {
                 const long long off = (long long)(2 * pr + h) * p.hop;
-                const int16_t* xf = xp + off;
+                const int16_t* xf = xp + off * p.sample_stride;
+                const long long qs = (long long)M * p.sample_stride; // column step in elements
                 if (all_samples) {
 #pragma unroll
-                    for (int q = 0; q < 16; q++) xr[16 * h + q] = pcm_to_float(xf + q * M);
+                    for (int q = 0; q < 16; q++) xr[16 * h + q] = pcm_to_float(xf + q * qs);
                 } else {
                     const long long s0 = cur.first_frame(p, F) * (long long)p.hop + off + t;
 #pragma unroll
-                    for (int q = 0; q < 16; q++) xr[16 * h + q] = (s0 + (long long)q * M < p.samples) ? pcm_to_float(xf + q * M) : 0.0f;
+                    for (int q = 0; q < 16; q++) xr[16 * h + q] = (s0 + (long long)q * M < p.samples) ? pcm_to_float(xf + q * qs) : 0.0f;
                 }
             }
         };

@@ -220,3 +220,21 @@ def test_fast_path_any_hop(oracle, lib, hop):
     # reference mode (no window, linear bins) through the same variant
     rcfg = lib.reference_config(4096, hop, 100)
     _check(oracle, lib, rcfg, pcm[:, :4096 + 40 * hop])
+
+
+@pytest.mark.parametrize("hop", [480, 512])
+def test_fast_path_interleaved_pcm(oracle, lib, hop):
+    """Interleaved PCM at N = 4096 goes through the fast kernel's own-samples variant; the arithmetic per frame is
+    that of the planar run, so the results are bit-identical (and the planar run is checked against the oracle)."""
+    cfg = lib.extended_config(4096, hop, 200)
+    pcm = oracle.synth_pcm(2, 4096 + 300 * hop + 5)
+    planar, _ = _check(oracle, lib, cfg, pcm)
+    with lib.BatchedSpectrum(cfg) as sp:
+        inter = sp.run(pcm.T.copy(), interleaved=True)
+        part = sp.run(pcm.T.copy(), 101, 250, interleaved=True)
+    assert (inter["bars"] == planar["bars"]).all()
+    assert (inter["bars_i32"] == planar["bars_i32"]).all()
+    for k in BEAT_FIELDS:
+        assert (inter["beat"][k] == planar["beat"][k]).all(), k
+        assert (part["beat"][k] == planar["beat"][k][:, 101:250]).all(), k
+    assert (part["bars"] == planar["bars"][:, 101:250]).all()

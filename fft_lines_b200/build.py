@@ -12,9 +12,14 @@ import sys
 HERE = os.path.dirname(os.path.abspath(__file__))
 CSRC = os.path.join(HERE, "csrc")
 LIB = os.path.join(HERE, "libfftlines_cuda.so")
-SOURCES = ["api.cu"]
-HEADERS = ["kernels.cuh", "fft_device.cuh", "stft_rdif.cuh", "stft_rdif_ws2.cuh", "stream.cuh", "../../include/fftlines.h", "../../include/fft_calculate.h",
-           "../../include/beatDetector.h", "../../include/fftl_complex.h"]
+# translation units: (source, extra defines, object name).  The fast path's template instantiations are the
+# bulk of the compile time; one unit per hop variant lets them build in parallel.
+UNITS = [("api.cu", [], "api"),
+         ("rdif_launch.cu", ["-DFFTL_RDIF_HOPQ=0"], "rdif_h0"), ("rdif_launch.cu", ["-DFFTL_RDIF_HOPQ=1"], "rdif_h1"),
+         ("rdif_launch.cu", ["-DFFTL_RDIF_HOPQ=2"], "rdif_h2"), ("rdif_launch.cu", ["-DFFTL_RDIF_HOPQ=4"], "rdif_h4")]
+SOURCES = sorted({u[0] for u in UNITS})
+HEADERS = ["kernels.cuh", "device_common.cuh", "fft_device.cuh", "stft_rdif.cuh", "stft_rdif_ws2.cuh", "rdif_launch.h", "stream.cuh", "../../include/fftlines.h",
+           "../../include/fft_calculate.h", "../../include/beatDetector.h", "../../include/fftl_complex.h"]
 
 
 def nvcc_path():
@@ -36,15 +41,34 @@ def build(force=False, verbose=False, extra=(), out=None):
     """out: alternative output path (developer A/B builds with extra -D flags)."""
     if out is None and not force and not needs_build():
         return LIB
-    cmd = [nvcc_path(), "-gencode", "arch=compute_100a,code=sm_100a", "-O3", "-lineinfo", "--use_fast_math",
-           "-std=c++17", "-shared", "-Xcompiler", "-fPIC,-O2,-fvisibility=default", "-cudart", "static",
-           "-o", out or LIB] + list(extra) + [os.path.join(CSRC, s) for s in SOURCES]
+    import tempfile
+    from concurrent.futures import ThreadPoolExecutor
+    target = out or LIB
+    common = [nvcc_path(), "-gencode", "arch=compute_100a,code=sm_100a", "-O3", "-lineinfo", "--use_fast_math",
+              "-std=c++17", "-Xcompiler", "-fPIC,-O2,-fvisibility=default"]
     if verbose:
-        cmd.insert(1, "-Xptxas")
-        cmd.insert(2, "-v")
-        print(" ".join(cmd))
-    subprocess.check_call(cmd)
-    return out or LIB
+        common += ["-Xptxas", "-v"]
+    with tempfile.TemporaryDirectory(prefix="fftl_build_") as tmp:
+        def compile_unit(unit):
+            src, defs, name = unit
+            obj = os.path.join(tmp, name + ".o")
+            cmd = common + list(extra) + defs + ["-c", os.path.join(CSRC, src), "-o", obj]
+            r = subprocess.run(cmd, stdout=subprocess.PIPE, stderr=subprocess.STDOUT, text=True)
+            return obj, cmd, r
+        with ThreadPoolExecutor(max_workers=min(len(UNITS), os.cpu_count() or 1)) as pool:
+            results = list(pool.map(compile_unit, UNITS))
+        for obj, cmd, r in results:
+            if verbose or r.returncode != 0:
+                print(" ".join(cmd))
+            if r.stdout.strip():
+                print(r.stdout, end="")
+            if r.returncode != 0:
+                raise subprocess.CalledProcessError(r.returncode, cmd)
+        link = [nvcc_path(), "-gencode", "arch=compute_100a,code=sm_100a", "-shared", "-cudart", "static", "-o", target] + [o for o, _, _ in results]
+        if verbose:
+            print(" ".join(link))
+        subprocess.check_call(link)
+    return target
 
 
 if __name__ == "__main__":

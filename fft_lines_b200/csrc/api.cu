@@ -13,7 +13,7 @@
 #include <vector>
 
 #include "kernels.cuh"
-#include "stft_rdif.cuh"
+#include "rdif_launch.h"
 #include "stft_rdif_ws2.cuh"
 #include "stream.cuh"
 #include "../../include/fft_calculate.h"
@@ -481,51 +481,6 @@ extern "C" int64_t fftl_stft_first_frame_needed(int64_t frame_begin, int32_t wit
 
 extern "C" int64_t fftl_stft_launch_count(const fftl_stft* h) { return h ? h->launches : 0; }
 
-// Tile bookkeeping of the fast path: tiles of F frames per channel and the tile ranges the kernel may treat
-// without edge handling (TileCursor).  False when a channel has too many tiles for the 32-bit cursor.
-static bool rdif_set_tiles(RdifParams& p, int channels, int F, int hopq)
-{
-    p.tiles_per_channel = (p.frame_end - p.frame0 + F - 1) / F;
-    p.total_tiles = p.tiles_per_channel * channels;
-    if (p.tiles_per_channel >= (1ll << 30)) return false;
-    const long long span = hopq ? (16 + (long long)hopq * (F - 1)) * 256 : (long long)(F - 1) * p.hop + 4096; // samples a tile reads per channel
-    const long long q = p.samples - span - p.frame0 * (long long)p.hop;
-    long long full = q < 0 ? 0 : q / ((long long)F * p.hop) + 1;                // tiles whose samples all exist
-    p.tic_full = (int)(full > p.tiles_per_channel ? p.tiles_per_channel : full);
-    p.tic_emit_lo = (int)((p.frame_emit - p.frame0 + F - 1) / F);               // first tile that starts at or after frame_emit
-    p.tic_emit_hi = (int)((p.frame_end - p.frame0) / F);                        // tiles that end at or before frame_end
-    return true;
-}
-
-// Fast path (stft_rdif.cuh).  Returns cudaErrorNotSupported when the configuration is not covered.
-template <int F, int HOPQ, bool WIN, int SGW, int ROWS>
-static cudaError_t launch_rdif(const fftl_stft* h, RdifParams p, int channels, cudaStream_t st)
-{
-    constexpr int MINB = 2; // two CTAs per SM is the design point (128 registers, <= 113 KB shared memory)
-    using Sh = RdifShape<4096, F>;
-    size_t smem = Sh::smem_bytes(p.bars_n, p.nseg, p.sg_half, ROWS);
-    if ((smem + 1024) * MINB > 228 * 1024) return cudaErrorNotSupported;
-    if (!rdif_set_tiles(p, channels, F, HOPQ)) return cudaErrorNotSupported;
-    if (p.total_tiles <= 0) return cudaSuccess;
-    auto kern = stft_bars_rdif_kernel<4096, F, HOPQ, WIN, true, MINB, SGW, ROWS>;
-    cudaError_t e = cudaFuncSetAttribute(kern, cudaFuncAttributeMaxDynamicSharedMemorySize, (int)smem);
-    if (e != cudaSuccess) return e;
-    long long grid = (long long)MINB * h->num_sms;
-    if (grid > p.total_tiles) grid = p.total_tiles;
-    kern<<<(unsigned)grid, Sh::THREADS, smem, st>>>(p);
-    return cudaGetLastError();
-}
-
-// magnitude rows kept: the smallest instantiated count that covers every bin a bar (or the bass bin) reads
-template <int HOPQ, bool WIN, int SGW>
-static cudaError_t launch_rdif_rows(const fftl_stft* h, const RdifParams& p, int channels, cudaStream_t st)
-{
-    if (p.mag_rows <= 1) return launch_rdif<4, HOPQ, WIN, SGW, 1>(h, p, channels, st);
-    if (p.mag_rows <= 4) return launch_rdif<4, HOPQ, WIN, SGW, 4>(h, p, channels, st);
-    if (p.mag_rows <= 7) return launch_rdif<4, HOPQ, WIN, SGW, 7>(h, p, channels, st);
-    return launch_rdif<4, HOPQ, WIN, SGW, 8>(h, p, channels, st);
-}
-
 template <int HOPQ, bool WIN, int SGW, int ROWS>
 static cudaError_t launch_rdif_ws2(const fftl_stft* h, RdifParams p, int channels, cudaStream_t st)
 {
@@ -543,19 +498,6 @@ static cudaError_t launch_rdif_ws2(const fftl_stft* h, RdifParams p, int channel
     return cudaGetLastError();
 }
 
-
-template <int HOPQ, bool WIN>
-static cudaError_t launch_rdif_sg(const fftl_stft* h, const RdifParams& p, int channels, cudaStream_t st)
-{
-#ifdef FFTL_GENERIC_SG
-    return launch_rdif_rows<HOPQ, WIN, -1>(h, p, channels, st);
-#endif
-    switch (p.sg_half) {
-    case 0: return launch_rdif_rows<HOPQ, WIN, 0>(h, p, channels, st);
-    case 3: return launch_rdif_rows<HOPQ, WIN, 3>(h, p, channels, st);
-    default: return launch_rdif_rows<HOPQ, WIN, -1>(h, p, channels, st);
-    }
-}
 
 static cudaError_t try_rdif(const fftl_stft* h, const StftParams& q, int channels, long long samples, cudaStream_t st)
 {
@@ -609,10 +551,10 @@ static cudaError_t try_rdif(const fftl_stft* h, const StftParams& q, int channel
         if (ew != cudaErrorNotSupported) return ew;
     }
     switch (hopq) {
-    case 0: return win ? launch_rdif_rows<0, true, -1>(h, p, channels, st) : launch_rdif_rows<0, false, -1>(h, p, channels, st);
-    case 1: return win ? launch_rdif_sg<1, true>(h, p, channels, st) : launch_rdif_sg<1, false>(h, p, channels, st);
-    case 2: return win ? launch_rdif_sg<2, true>(h, p, channels, st) : launch_rdif_sg<2, false>(h, p, channels, st);
-    default: return win ? launch_rdif_sg<4, true>(h, p, channels, st) : launch_rdif_sg<4, false>(h, p, channels, st);
+    case 0: return launch_rdif_h0(win, h->num_sms, p, channels, st);
+    case 1: return launch_rdif_h1(win, h->num_sms, p, channels, st);
+    case 2: return launch_rdif_h2(win, h->num_sms, p, channels, st);
+    default: return launch_rdif_h4(win, h->num_sms, p, channels, st);
     }
 }
 

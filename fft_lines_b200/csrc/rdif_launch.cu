@@ -1,0 +1,67 @@
+// rdif_launch.cu -- instantiations and launchers of the fast path for ONE hop variant
+// (-DFFTL_RDIF_HOPQ=0|1|2|4; see rdif_launch.h).
+#include <cuda_runtime.h>
+#include "rdif_launch.h"
+
+#ifndef FFTL_RDIF_HOPQ
+#error "compile with -DFFTL_RDIF_HOPQ=0|1|2|4"
+#endif
+
+namespace fftl {
+
+// Fast path (stft_rdif.cuh).  Returns cudaErrorNotSupported when the configuration is not covered.
+template <int F, int HOPQ, bool WIN, int SGW, int ROWS>
+static cudaError_t launch_rdif(int num_sms, RdifParams p, int channels, cudaStream_t st)
+{
+    constexpr int MINB = 2; // two CTAs per SM is the design point (128 registers, <= 113 KB shared memory)
+    using Sh = RdifShape<4096, F>;
+    size_t smem = Sh::smem_bytes(p.bars_n, p.nseg, p.sg_half, ROWS);
+    if ((smem + 1024) * MINB > 228 * 1024) return cudaErrorNotSupported;
+    if (!rdif_set_tiles(p, channels, F, HOPQ)) return cudaErrorNotSupported;
+    if (p.total_tiles <= 0) return cudaSuccess;
+    auto kern = stft_bars_rdif_kernel<4096, F, HOPQ, WIN, true, MINB, SGW, ROWS>;
+    cudaError_t e = cudaFuncSetAttribute(kern, cudaFuncAttributeMaxDynamicSharedMemorySize, (int)smem);
+    if (e != cudaSuccess) return e;
+    long long grid = (long long)MINB * num_sms;
+    if (grid > p.total_tiles) grid = p.total_tiles;
+    kern<<<(unsigned)grid, Sh::THREADS, smem, st>>>(p);
+    return cudaGetLastError();
+}
+
+// magnitude rows kept: the smallest instantiated count that covers every bin a bar (or the bass bin) reads
+template <int HOPQ, bool WIN, int SGW>
+static cudaError_t launch_rdif_rows(int num_sms, const RdifParams& p, int channels, cudaStream_t st)
+{
+    if (p.mag_rows <= 1) return launch_rdif<4, HOPQ, WIN, SGW, 1>(num_sms, p, channels, st);
+    if (p.mag_rows <= 4) return launch_rdif<4, HOPQ, WIN, SGW, 4>(num_sms, p, channels, st);
+    if (p.mag_rows <= 7) return launch_rdif<4, HOPQ, WIN, SGW, 7>(num_sms, p, channels, st);
+    return launch_rdif<4, HOPQ, WIN, SGW, 8>(num_sms, p, channels, st);
+}
+
+template <int HOPQ, bool WIN>
+static cudaError_t launch_rdif_sg(int num_sms, const RdifParams& p, int channels, cudaStream_t st)
+{
+#ifdef FFTL_GENERIC_SG
+    return launch_rdif_rows<HOPQ, WIN, -1>(num_sms, p, channels, st);
+#endif
+    switch (p.sg_half) {
+    case 0: return launch_rdif_rows<HOPQ, WIN, 0>(num_sms, p, channels, st);
+    case 3: return launch_rdif_rows<HOPQ, WIN, 3>(num_sms, p, channels, st);
+    default: return launch_rdif_rows<HOPQ, WIN, -1>(num_sms, p, channels, st);
+    }
+}
+
+
+#define FFTL_CAT2(a, b) a##b
+#define FFTL_CAT(a, b) FFTL_CAT2(a, b)
+cudaError_t FFTL_CAT(launch_rdif_h, FFTL_RDIF_HOPQ)(bool win, int num_sms, const RdifParams& p, int channels, cudaStream_t st)
+{
+#if FFTL_RDIF_HOPQ == 0
+    // the own-samples variant is built with the run-time Savitzky-Golay width only
+    return win ? launch_rdif_rows<0, true, -1>(num_sms, p, channels, st) : launch_rdif_rows<0, false, -1>(num_sms, p, channels, st);
+#else
+    return win ? launch_rdif_sg<FFTL_RDIF_HOPQ, true>(num_sms, p, channels, st) : launch_rdif_sg<FFTL_RDIF_HOPQ, false>(num_sms, p, channels, st);
+#endif
+}
+
+} // namespace fftl

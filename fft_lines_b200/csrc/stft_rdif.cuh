@@ -21,7 +21,7 @@
 // here for a tile of F frames per CTA iteration; CTAs are persistent.
 // Shared memory per frame: 8 slots * M complex (+1/16 padding) + N/2+1 magnitudes.
 #pragma once
-#include "kernels.cuh"
+#include "device_common.cuh"
 
 namespace fftl {
 

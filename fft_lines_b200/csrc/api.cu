@@ -502,11 +502,13 @@ static cudaError_t launch_rdif_ws2(const fftl_stft* h, RdifParams p, int channel
 static cudaError_t try_rdif(const fftl_stft* h, const StftParams& q, int channels, long long samples, cudaStream_t st)
 {
     const fftl_config& c = h->cfg;
-    if (c.n != 4096) return cudaErrorNotSupported;
-    // hop = 256, 512 or 1024 on planar PCM: the frames of a tile share their samples in registers; any other
-    // hop, or interleaved PCM: the variant in which every frame loads its own (hopq = 0)
-    int hopq = (c.hop % 256) == 0 ? c.hop / 256 : 0;
-    if ((hopq != 1 && hopq != 2 && hopq != 4) || q.sample_stride != 1) hopq = 0;
+    if (c.n != 4096 && c.n != 2048) return cudaErrorNotSupported;
+    // hop = 1, 2 or 4 columns (n/16 samples) on planar PCM: the frames of a tile share their samples in registers;
+    // any other hop, or interleaved PCM: the variant in which every frame loads its own (hopq = 0).
+    // n = 2048 is built for hop 512 (4 columns) and the own-samples variant.
+    const int M = c.n / 16;
+    int hopq = (c.hop % M) == 0 ? c.hop / M : 0;
+    if ((hopq != 1 && hopq != 2 && hopq != 4) || q.sample_stride != 1 || (c.n == 2048 && hopq != 4)) hopq = 0;
     if (getenv("FFTL_DISABLE_RDIF") || !h->seg_packable) return cudaErrorNotSupported;
     RdifParams p;
     memset(&p, 0, sizeof(p));
@@ -538,9 +540,10 @@ static cudaError_t try_rdif(const fftl_stft* h, const StftParams& q, int channel
     p.sg_half = q.sg_half;
     p.strict = q.strict;
     p.bass_bin = q.bass_bin;
-    p.mag_rows = (h->mag_bins + 255) / 256;       // bins < 256*rows are kept; 8 rows also keep bin N/2
-    if (p.mag_rows > 8 || h->mag_bins > 2048) p.mag_rows = 8;
-    p.mag_stride = RdifShape<4096, 4>::mag_stride(p.mag_rows);
+    const int full_rows = c.n / 512;
+    p.mag_rows = (h->mag_bins + 255) / 256;       // bins < 256*rows are kept; all rows also keep bin N/2
+    if (p.mag_rows > full_rows || h->mag_bins > c.n / 2) p.mag_rows = full_rows;
+    p.mag_stride = c.n == 4096 ? RdifShape<4096, 4>::mag_stride(p.mag_rows) : RdifShape<2048, 4>::mag_stride(p.mag_rows);
     for (int i = 0; i < 4; i++) p.beat_bars[i] = q.beat_bars[i];
     p.zoom = q.zoom;
     p.circle_add = q.circle_add;
@@ -551,10 +554,10 @@ static cudaError_t try_rdif(const fftl_stft* h, const StftParams& q, int channel
         if (ew != cudaErrorNotSupported) return ew;
     }
     switch (hopq) {
-    case 0: return launch_rdif_h0(win, h->num_sms, p, channels, st);
-    case 1: return launch_rdif_h1(win, h->num_sms, p, channels, st);
-    case 2: return launch_rdif_h2(win, h->num_sms, p, channels, st);
-    default: return launch_rdif_h4(win, h->num_sms, p, channels, st);
+    case 0: return launch_rdif_h0(c.n, win, h->num_sms, p, channels, st);
+    case 1: return launch_rdif_h1(c.n, win, h->num_sms, p, channels, st);
+    case 2: return launch_rdif_h2(c.n, win, h->num_sms, p, channels, st);
+    default: return launch_rdif_h4(c.n, win, h->num_sms, p, channels, st);
     }
 }
 

@@ -10,16 +10,18 @@
 namespace fftl {
 
 // Fast path (stft_rdif.cuh).  Returns cudaErrorNotSupported when the configuration is not covered.
-template <int F, int HOPQ, bool WIN, int SGW, int ROWS>
+template <int N, int F, int HOPQ, bool WIN, int SGW, int ROWS>
 static cudaError_t launch_rdif(int num_sms, RdifParams p, int channels, cudaStream_t st)
 {
-    constexpr int MINB = 2; // two CTAs per SM is the design point (128 registers, <= 113 KB shared memory)
-    using Sh = RdifShape<4096, F>;
+    // design points: N = 4096: two CTAs of 256 threads per SM (128 registers, <= 113 KB shared memory each);
+    // N = 2048: four CTAs of 128 threads (three when the tables are large)
+    constexpr int MINB = N == 4096 ? 2 : 4;
+    using Sh = RdifShape<N, F>;
     size_t smem = Sh::smem_bytes(p.bars_n, p.nseg, p.sg_half, ROWS);
-    if ((smem + 1024) * MINB > 228 * 1024) return cudaErrorNotSupported;
-    if (!rdif_set_tiles(p, channels, F, HOPQ)) return cudaErrorNotSupported;
+    if ((smem + 1024) * (MINB == 2 ? 2 : 3) > 228 * 1024) return cudaErrorNotSupported;
+    if (!rdif_set_tiles(p, channels, F, HOPQ, N)) return cudaErrorNotSupported;
     if (p.total_tiles <= 0) return cudaSuccess;
-    auto kern = stft_bars_rdif_kernel<4096, F, HOPQ, WIN, true, MINB, SGW, ROWS>;
+    auto kern = stft_bars_rdif_kernel<N, F, HOPQ, WIN, true, MINB, SGW, ROWS>;
     cudaError_t e = cudaFuncSetAttribute(kern, cudaFuncAttributeMaxDynamicSharedMemorySize, (int)smem);
     if (e != cudaSuccess) return e;
     long long grid = (long long)MINB * num_sms;
@@ -32,10 +34,18 @@ static cudaError_t launch_rdif(int num_sms, RdifParams p, int channels, cudaStre
 template <int HOPQ, bool WIN, int SGW>
 static cudaError_t launch_rdif_rows(int num_sms, const RdifParams& p, int channels, cudaStream_t st)
 {
-    if (p.mag_rows <= 1) return launch_rdif<4, HOPQ, WIN, SGW, 1>(num_sms, p, channels, st);
-    if (p.mag_rows <= 4) return launch_rdif<4, HOPQ, WIN, SGW, 4>(num_sms, p, channels, st);
-    if (p.mag_rows <= 7) return launch_rdif<4, HOPQ, WIN, SGW, 7>(num_sms, p, channels, st);
-    return launch_rdif<4, HOPQ, WIN, SGW, 8>(num_sms, p, channels, st);
+    if (p.mag_rows <= 1) return launch_rdif<4096, 4, HOPQ, WIN, SGW, 1>(num_sms, p, channels, st);
+    if (p.mag_rows <= 4) return launch_rdif<4096, 4, HOPQ, WIN, SGW, 4>(num_sms, p, channels, st);
+    if (p.mag_rows <= 7) return launch_rdif<4096, 4, HOPQ, WIN, SGW, 7>(num_sms, p, channels, st);
+    return launch_rdif<4096, 4, HOPQ, WIN, SGW, 8>(num_sms, p, channels, st);
+}
+
+// N = 2048 (the reference's own size, global.h:3): run-time Savitzky-Golay width, one row or the full band
+template <int HOPQ, bool WIN>
+static cudaError_t launch_rdif_2k(int num_sms, const RdifParams& p, int channels, cudaStream_t st)
+{
+    if (p.mag_rows <= 1) return launch_rdif<2048, 4, HOPQ, WIN, -1, 1>(num_sms, p, channels, st);
+    return launch_rdif<2048, 4, HOPQ, WIN, -1, 4>(num_sms, p, channels, st);
 }
 
 template <int HOPQ, bool WIN>
@@ -54,8 +64,15 @@ static cudaError_t launch_rdif_sg(int num_sms, const RdifParams& p, int channels
 
 #define FFTL_CAT2(a, b) a##b
 #define FFTL_CAT(a, b) FFTL_CAT2(a, b)
-cudaError_t FFTL_CAT(launch_rdif_h, FFTL_RDIF_HOPQ)(bool win, int num_sms, const RdifParams& p, int channels, cudaStream_t st)
+cudaError_t FFTL_CAT(launch_rdif_h, FFTL_RDIF_HOPQ)(int n, bool win, int num_sms, const RdifParams& p, int channels, cudaStream_t st)
 {
+    if (n == 2048) {
+#if FFTL_RDIF_HOPQ == 0 || FFTL_RDIF_HOPQ == 4
+        return win ? launch_rdif_2k<FFTL_RDIF_HOPQ, true>(num_sms, p, channels, st) : launch_rdif_2k<FFTL_RDIF_HOPQ, false>(num_sms, p, channels, st);
+#else
+        return cudaErrorNotSupported;
+#endif
+    }
 #if FFTL_RDIF_HOPQ == 0
     // the own-samples variant is built with the run-time Savitzky-Golay width only
     return win ? launch_rdif_rows<0, true, -1>(num_sms, p, channels, st) : launch_rdif_rows<0, false, -1>(num_sms, p, channels, st);

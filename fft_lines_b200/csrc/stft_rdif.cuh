@@ -112,7 +112,8 @@ template <int N, int F> struct RdifShape {
     // bin -> bin + bin/16: the 16 lanes of a sub-transform (bins 16 apart) then hit 16 distinct
     // even banks, the other half-warp (odd frame) the odd ones
     // Only the 256-bin rows a configuration reads are kept (mag_rows of them; all 8 plus bin N/2 for full band).
-    __host__ __device__ static constexpr int mag_stride(int mag_rows) { return padded_size(mag_rows >= 8 ? NB : 256 * mag_rows) + 3; }
+    static constexpr int FULL_ROWS = N / 512;        // 256-bin rows below N/2 (8 at N = 4096, 4 at N = 2048)
+    __host__ __device__ static constexpr int mag_stride(int mag_rows) { return padded_size(mag_rows >= FULL_ROWS ? NB : 256 * mag_rows) + 3; }
     __host__ __device__ static size_t tail_bytes(int bars, int nseg) { return (size_t)(nseg + bars) * F * sizeof(float); }
     // per-CTA copies of the tail's tables (the L1 is tiny next to 105 KB of shared memory and is
     // streamed through by the PCM, so table loads from global would pay L2 latency in every tail phase)
@@ -396,7 +397,7 @@ __global__ void __launch_bounds__(RdifShape<N, F>::THREADS, MINB) stft_bars_rdif
     using Sh = RdifShape<N, F>;
     constexpr int M = Sh::M, SUBG = Sh::SUBG, SLOT = Sh::SLOT;
     constexpr int MAGS = Sh::mag_stride(ROWS);
-    static_assert(N == 4096, "this instantiation covers N = 4096 (M = 256, two radix-16 sub-passes)");
+    static_assert(N == 4096 || N == 2048, "N = 16 M with M = 256 (two radix-16 sub-passes) or M = 128 (radix 16, then radix 8)");
     static_assert(F == 2 || F == 4, "frames are packed in pairs; the tail moves F floats as one vector");
     // HOPQ > 0: hop = HOPQ*M, the tile's frames share their samples (NX per column per tile).
     // HOPQ = 0: any hop; every frame loads its own 16 samples per column, one frame pair (32) at a time.
@@ -440,8 +441,15 @@ __global__ void __launch_bounds__(RdifShape<N, F>::THREADS, MINB) stft_bars_rdif
         }
 #pragma unroll
         for (int k0 = 1; k0 <= 8; k0++) twa[k0] = __ldg(p.tw + t * k0);
+        if (M == 256) {
 #pragma unroll
-        for (int r = 1; r < 16; r++) twc[r] = __ldg(p.twm + j * r);
+            for (int r = 1; r < 16; r++) twc[r] = __ldg(p.twm + j * r);
+        } else { // M = 128: second sub-pass is two radix-8 butterflies per lane, jj = j + 8 tt: W_128^(jj r), r = 1..7
+#pragma unroll
+            for (int tt = 0; tt < 2; tt++)
+#pragma unroll
+                for (int r = 1; r < 8; r++) twc[8 * tt + r] = __ldg(p.twm + (((j + 8 * tt) * r) & (M - 1)));
+        }
     }
 
     TileCursor cur;
@@ -511,7 +519,7 @@ __global__ void __launch_bounds__(RdifShape<N, F>::THREADS, MINB) stft_bars_rdif
         };
         // pass B/C of frame pair pr: one slot per half-warp, warp-level syncs only
         auto wsync = [] { __syncwarp(); };
-        auto pass_bc = [&](const int pr) {
+        auto pass_bc256 = [&](const int pr) {
             float2* s = slots + (pr * 16 + hw) * SLOT;
             float2 v[16];
             // first sub-pass (no twiddles): radix 16 over t = j + 16 r, result X1[16 j + k] back into the slot
@@ -578,6 +586,85 @@ __global__ void __launch_bounds__(RdifShape<N, F>::THREADS, MINB) stft_bars_rdif
                     mg2[pad_index(N / 2)] = make_float2(fabsf(v[rr].x), fabsf(v[rr].y));
                 }
             }
+        };
+        // M = 128 (N = 2048): 8 lanes per slot, radix 16 then two radix-8 butterflies per lane
+        auto pass_bc128 = [&](const int pr) {
+            float2* s = slots + (pr * 16 + hw) * SLOT;
+            float2 v[16];
+#pragma unroll
+            for (int r = 0; r < 16; r++) v[r] = s[pad_index(j + r * SUBG)];
+            radix16_fused<false>(v, nullptr);
+            wsync();
+#pragma unroll
+            for (int rr = 0; rr < 16; rr++) s[pad_index(16 * j + Radix<16>::out_index(rr))] = v[rr];
+            wsync();
+#pragma unroll
+            for (int tt = 0; tt < 2; tt++) {
+#pragma unroll
+                for (int r = 0; r < 8; r++) v[8 * tt + r] = s[pad_index((j + 8 * tt) + 16 * r)];
+#pragma unroll
+                for (int r = 1; r < 8; r++) v[8 * tt + r] = cmul(v[8 * tt + r], RESIDENT ? twc[8 * tt + r] : ldg_pinned(p.twm + (((j + 8 * tt) * r) & (M - 1))));
+                Radix<8>::run(v + 8 * tt);
+            }
+            // v[8 tt + rr] = Z[m], m = jj + 16 kk, jj = j + 8 tt, kk = Radix<8>::out_index(rr); register of kk: ((kk&3)<<1)|(kk>>2)
+            float2* mg2 = mags + pr * MAGS;
+            if (hw >= 2) {
+                // regular slot: m < 64 directly (bin k0 + 16 m), m >= 64 through the conjugate mirror (16-k0) + 16 (127-m)
+                const int k0 = hw >> 1;
+                float* mg = reinterpret_cast<float*>(mg2) + (hw & 1);
+#pragma unroll
+                for (int tt = 0; tt < 2; tt++) {
+                    const int jj = j + 8 * tt;
+                    float* lo_base = mg + 2 * (k0 + 17 * jj);
+                    float* hi_base = mg + 2 * ((16 - k0) + 17 * (15 - jj));
+#pragma unroll
+                    for (int rr = 0; rr < 8; rr++) {
+                        const int kk = Radix<8>::out_index(rr);
+                        const int c = kk < 4 ? kk : 7 - kk;
+                        if (c < ROWS) {
+                            const float2 z = v[8 * tt + rr];
+                            const float mag = sqrtf(fmaf(z.x, z.x, z.y * z.y));
+                            if (kk < 4) lo_base[2 * 272 * c] = mag;
+                            else hi_base[2 * 272 * c] = mag;
+                        }
+                    }
+                }
+            } else {
+                // packed slot (hw 0: residue 0, partner m' = 128-m; hw 1: residue 8, partner m' = 127-m): the partner of
+                // (jj, kk) is (15-jj, 7-kk) for hw 1 and (16-jj, 7-kk) for hw 0, i.e. the other tt of lane 7-j / 8-j;
+                // lane 0 of hw 0 is its own partner: (8, 7-kk) for jj = 8 and (0, (8-kk)&7) for jj = 0
+                const int src = hw ? (7 - j) : ((8 - j) & 7);
+                const bool self = (hw == 0) && (j == 0);
+#pragma unroll
+                for (int tt = 0; tt < 2; tt++) {
+#pragma unroll
+                    for (int kk = 0; kk < (ROWS < 4 ? ROWS : 4); kk++) {
+                        const int rr = ((kk & 3) << 1) | (kk >> 2);
+                        const int kp = 7 - kk, rp = ((kp & 3) << 1) | (kp >> 2);
+                        float pr_ = __shfl_sync(0x0000ffffu, v[8 * (1 - tt) + rp].x, src, 8);
+                        float pi_ = __shfl_sync(0x0000ffffu, v[8 * (1 - tt) + rp].y, src, 8);
+                        if (self) {
+                            const int ks = (8 - kk) & 7, rs = ((ks & 3) << 1) | (ks >> 2);
+                            pr_ = tt ? v[8 + rp].x : v[rs].x;
+                            pi_ = tt ? v[8 + rp].y : v[rs].y;
+                        }
+                        const float2 z = v[8 * tt + rr];
+                        float ar = z.x + pr_, ai = z.y - pi_; // 2 * Xa
+                        float br = z.x - pr_, bi = z.y + pi_; // 2i * Xb
+                        const int bin = 16 * ((j + 8 * tt) + 16 * kk) + (hw ? 8 : 0);
+                        mg2[pad_index(bin)] = make_float2(0.5f * sqrtf(fmaf(ar, ar, ai * ai)), 0.5f * sqrtf(fmaf(br, br, bi * bi)));
+                    }
+                }
+                if (self && ROWS >= 4) {
+                    // m = 64 (bin N/2) is its own partner: Z[64] = Xa[N/2] + i Xb[N/2], both real; jj = 0, kk = 4
+                    const int rr = ((4 & 3) << 1) | (4 >> 2);
+                    mg2[pad_index(N / 2)] = make_float2(fabsf(v[rr].x), fabsf(v[rr].y));
+                }
+            }
+        };
+        auto pass_bc = [&](const int pr) {
+            if constexpr (M == 256) pass_bc256(pr);
+            else pass_bc128(pr);
         };
         // Order of work and CTA barriers: pass B/C of a pair needs pass A of that pair from every thread.
         //   A(0) | A(1) | B/C(0) B/C(1) | tail      (F = 4)          A(0) | B/C(0) | tail      (F = 2)

@@ -238,3 +238,33 @@ def test_fast_path_interleaved_pcm(oracle, lib, hop):
         assert (inter["beat"][k] == planar["beat"][k]).all(), k
         assert (part["beat"][k] == planar["beat"][k][:, 101:250]).all(), k
     assert (part["bars"] == planar["bars"][:, 101:250]).all()
+
+
+@pytest.mark.parametrize("n", [2048, 4096])
+def test_fast_path_variants_both_sizes(oracle, lib, n):
+    """The real-input fast path at the reference's own N = 2048 (global.h:3) and at 4096: shared-sample variant
+    (hop 512), own-sample variant (hop 300), windowed and not, one magnitude row and the full band including
+    bin N/2, each against the oracle, against the generic kernel and shard == full."""
+    import os
+    pcm = oracle.synth_pcm(2, n + 150 * 512 + 3)
+    cfgs = [lib.extended_config(n, 512, 100),                       # Hann, log bins to 20 kHz, SG
+            lib.extended_config(n, 512, 64, fmax=2000.0),           # few magnitude rows
+            lib.extended_config(n, 300, 100, sg_half=0),            # own-sample variant, no smoothing
+            lib.reference_config(n, 512, n // 2 + 1),               # every bin including N/2 (bars = N/2 + 1)
+            lib.reference_config(n, 512, 100, circle=1)]
+    for cfg in cfgs:
+        got, _ = _check(oracle, lib, cfg, pcm)
+        with lib.BatchedSpectrum(cfg) as sp:
+            part = sp.run(pcm, 33, 140)
+            os.environ["FFTL_DISABLE_RDIF"] = "1"
+            try:
+                gen = sp.run(pcm)
+            finally:
+                del os.environ["FFTL_DISABLE_RDIF"]
+        assert (part["bars"] == got["bars"][:, 33:140]).all()
+        for k in BEAT_FIELDS:
+            assert (part["beat"][k] == got["beat"][k][:, 33:140]).all(), k
+        # two fp32 transforms with different operation orders: rounding relative to the largest BIN of the frame,
+        # which a band-limited bar set need not contain
+        fmax = np.abs(gen["bars"]).max(axis=-1, keepdims=True)
+        assert (np.abs(gen["bars"] - got["bars"]) <= 1e-5 * fmax).all()

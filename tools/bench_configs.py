@@ -38,7 +38,7 @@ F.synth_pcm_device(pcm)
 with F.BatchedSpectrum(F.reference_config(2048, 512, 100)) as sp:
     frames, ms, bms = timed_device(sp, pcm)
 out.append({"config": "c1: 10 s stereo 48 kHz, 2048-pt, hop 512 (assumed), 100 bars, reference mode", "frames": frames,
-            "ms": ms, "bars_kernel_ms": bms, "frames_per_s": frames / ms * 1e3, "kernel": "stft_bars_kernel<2048> (generic)"})
+            "ms": ms, "bars_kernel_ms": bms, "frames_per_s": frames / ms * 1e3, "kernel": "stft_bars_rdif_kernel<2048> (fast path, hop 512)"})
 
 # ---- c3: 1024 concurrent mono streams, 1024-pt window, 64 bars: one tick (512 new samples per stream) per batch
 # through the streaming front end (device-resident sliding windows + beat state)

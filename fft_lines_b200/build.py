@@ -18,7 +18,7 @@ UNITS = [("api.cu", [], "api"),
          ("rdif_launch.cu", ["-DFFTL_RDIF_HOPQ=0"], "rdif_h0"), ("rdif_launch.cu", ["-DFFTL_RDIF_HOPQ=1"], "rdif_h1"),
          ("rdif_launch.cu", ["-DFFTL_RDIF_HOPQ=2"], "rdif_h2"), ("rdif_launch.cu", ["-DFFTL_RDIF_HOPQ=4"], "rdif_h4")]
 SOURCES = sorted({u[0] for u in UNITS})
-HEADERS = ["kernels.cuh", "device_common.cuh", "fft_device.cuh", "stft_rdif.cuh", "stft_rdif_ws2.cuh", "rdif_launch.h", "stream.cuh", "../../include/fftlines.h",
+HEADERS = ["kernels.cuh", "device_common.cuh", "fft_device.cuh", "stft_rdif.cuh", "rdif_launch.h", "stream.cuh", "../../include/fftlines.h",
            "../../include/fft_calculate.h", "../../include/beatDetector.h", "../../include/fftl_complex.h"]
 
 

@@ -14,7 +14,6 @@
 
 #include "kernels.cuh"
 #include "rdif_launch.h"
-#include "stft_rdif_ws2.cuh"
 #include "stream.cuh"
 #include "../../include/fft_calculate.h"
 #include "../../include/beatDetector.h"
@@ -481,24 +480,6 @@ extern "C" int64_t fftl_stft_first_frame_needed(int64_t frame_begin, int32_t wit
 
 extern "C" int64_t fftl_stft_launch_count(const fftl_stft* h) { return h ? h->launches : 0; }
 
-template <int HOPQ, bool WIN, int SGW, int ROWS>
-static cudaError_t launch_rdif_ws2(const fftl_stft* h, RdifParams p, int channels, cudaStream_t st)
-{
-    using Sh = RdifWs2Shape<ROWS>;
-    size_t smem = Sh::smem_bytes(p.bars_n, p.nseg, p.sg_half);
-    if (smem > 227 * 1024) return cudaErrorNotSupported;
-    if (!rdif_set_tiles(p, channels, Sh::F, HOPQ)) return cudaErrorNotSupported;
-    if (p.total_tiles <= 0) return cudaSuccess;
-    auto kern = stft_bars_rdif_ws2_kernel<HOPQ, WIN, SGW, ROWS>;
-    cudaError_t e = cudaFuncSetAttribute(kern, cudaFuncAttributeMaxDynamicSharedMemorySize, (int)smem);
-    if (e != cudaSuccess) return e;
-    long long grid = h->num_sms; // one persistent CTA per SM, two transform groups each
-    if (grid * 2 > p.total_tiles) grid = (p.total_tiles + 1) / 2;
-    kern<<<(unsigned)grid, Sh::THREADS, smem, st>>>(p);
-    return cudaGetLastError();
-}
-
-
 static cudaError_t try_rdif(const fftl_stft* h, const StftParams& q, int channels, long long samples, cudaStream_t st)
 {
     const fftl_config& c = h->cfg;
@@ -548,11 +529,6 @@ static cudaError_t try_rdif(const fftl_stft* h, const StftParams& q, int channel
     p.zoom = q.zoom;
     p.circle_add = q.circle_add;
     const bool win = q.window != nullptr;
-    static const bool usews2 = getenv("FFTL_RDIF_WS2") != nullptr; // developer A/B switch (experimental: HOPQ 2, SG 3, Hann)
-    if (usews2 && hopq == 2 && p.sg_half == 3 && win) {
-        cudaError_t ew = p.mag_rows <= 7 ? launch_rdif_ws2<2, true, 3, 7>(h, p, channels, st) : launch_rdif_ws2<2, true, 3, 8>(h, p, channels, st);
-        if (ew != cudaErrorNotSupported) return ew;
-    }
     switch (hopq) {
     case 0: return launch_rdif_h0(c.n, win, h->num_sms, p, channels, st);
     case 1: return launch_rdif_h1(c.n, win, h->num_sms, p, channels, st);

@@ -40,6 +40,19 @@ with F.BatchedSpectrum(F.reference_config(2048, 512, 100)) as sp:
 out.append({"config": "c1: 10 s stereo 48 kHz, 2048-pt, hop 512 (assumed), 100 bars, reference mode", "frames": frames,
             "ms": ms, "bars_kernel_ms": bms, "frames_per_s": frames / ms * 1e3, "kernel": "stft_bars_rdif_kernel<2048> (fast path, hop 512)"})
 
+# ---- c1 scaled up: the reference's configuration on 1 h of stereo audio (batch throughput of the N = 2048 fast path)
+pcm = torch.empty((2, 48000 * 3600), dtype=torch.int16, device=dev)
+F.synth_pcm_device(pcm)
+for label, cfg in (("reference mode (no window, bar i = bin i)", F.reference_config(2048, 512, 100)),
+                   ("extended mode (Hann, 100 log bars, SG)", F.extended_config(2048, 512, 100))):
+    with F.BatchedSpectrum(cfg) as sp:
+        frames, ms, bms = timed_device(sp, pcm)
+    out.append({"config": "c1 x 360: 1 h stereo 48 kHz, 2048-pt, hop 512, 100 bars + beat, " + label, "frames": frames, "ms": ms,
+                "bars_kernel_ms": bms, "frames_per_s": frames / ms * 1e3, "bars_kernel_frames_per_s": frames / bms * 1e3,
+                "roofline_frac_nominal_fp32": frames / bms * 1e3 * 5 * 2048 * 11 / 74.45e12,
+                "kernel": "stft_bars_rdif_kernel<2048> (fast path, hop 512)"})
+del pcm
+
 # ---- c3: 1024 concurrent mono streams, 1024-pt window, 64 bars: one tick (512 new samples per stream) per batch
 # through the streaming front end (device-resident sliding windows + beat state)
 STREAMS, COUNT = 1024, 512

@@ -268,3 +268,13 @@ def test_fast_path_variants_both_sizes(oracle, lib, n):
         # which a band-limited bar set need not contain
         fmax = np.abs(gen["bars"]).max(axis=-1, keepdims=True)
         assert (np.abs(gen["bars"] - got["bars"]) <= 1e-5 * fmax).all()
+
+
+@pytest.mark.parametrize("n,hop", [(4096, 512), (2048, 512), (4096, 480)])
+def test_fast_path_many_channels_few_frames(oracle, lib, n, hop):
+    """More CTAs than a channel has tiles: the persistent kernel's tile cursor steps over several channels at once,
+    and the last tile of every channel is ragged (9 frames = 2 tiles + 1 frame)."""
+    channels = 37
+    pcm = oracle.synth_pcm(channels, n + 8 * hop + 11)
+    _check(oracle, lib, lib.extended_config(n, hop, 100), pcm)
+    _check(oracle, lib, lib.reference_config(n, hop, 100), pcm, 3, 8)

@@ -488,7 +488,7 @@ static cudaError_t try_rdif(const fftl_stft* h, const StftParams& q, int channel
     // any other hop, or interleaved PCM: the variant in which every frame loads its own (hopq = 0).
     // n = 2048 is built for hop 512 (4 columns) and the own-samples variant.
     const int M = c.n / 16;
-    int hopq = (c.hop % M) == 0 ? c.hop / M : 0;
+    int hopq = (q.hop % M) == 0 ? q.hop / M : 0; // q.hop: the caller's hop (the streaming front end passes n: one frame per window)
     if ((hopq != 1 && hopq != 2 && hopq != 4) || q.sample_stride != 1 || (c.n == 2048 && hopq != 4)) hopq = 0;
     if (getenv("FFTL_DISABLE_RDIF") || !h->seg_packable) return cudaErrorNotSupported;
     RdifParams p;
@@ -542,7 +542,7 @@ static cudaError_t try_rdif(const fftl_stft* h, const StftParams& q, int channel
 // starts computing aux (frames before it must already be in the aux arrays).
 static int run_range(fftl_stft* h, const int16_t* pcm, int channels, int64_t cstride, int64_t sstride, int64_t samples, int64_t frames_total, int64_t compute_from,
                      int64_t fb, int64_t fe, int64_t out_base, int64_t nf_emit, int64_t aux_base, int64_t nf_aux, float* bars,
-                     int32_t* bars_i32, bool aux, fftl_beat* beat, cudaStream_t st, cudaEvent_t* evs, bool force_generic = false)
+                     int32_t* bars_i32, bool aux, fftl_beat* beat, cudaStream_t st, cudaEvent_t* evs, bool force_generic = false, int hop_override = 0)
 {
     const fftl_config& c = h->cfg;
     StftParams p;
@@ -567,7 +567,7 @@ static int run_range(fftl_stft* h, const int16_t* pcm, int channels, int64_t cst
     p.bars_i32 = bars_i32 ? bars_i32 + (fb - out_base) * (int64_t)c.bars : nullptr;
     p.aux_w = aux ? h->d_aux : nullptr;
     p.aux_bass = aux ? h->d_aux + (size_t)channels * nf_aux : nullptr;
-    p.hop = c.hop;
+    p.hop = hop_override ? hop_override : c.hop;
     p.bars_n = c.bars;
     p.sg_half = c.sg_half;
     p.strict = c.strict_int;
@@ -982,8 +982,18 @@ extern "C" int fftl_stream_push_device(fftl_stream* s, const int16_t* fresh, int
     else
         stream_slide_kernel<<<s->streams, 256, 0, st>>>(s->d_window, fresh, c.n, count, stride, s->move_mode == FFTL_MOVE_REFERENCE);
     CUDA_TRY(cudaGetLastError());
-    // one frame per stream: channels = streams, samples = n
-    int rc = run_range(h, s->d_window, s->streams, c.n, 1, c.n, 1, 0, 0, 1, 0, 1, 0, 1, bars, bars_i32, true, nullptr, st, nullptr, true);
+    int rc;
+    if (c.n == 4096 || c.n == 2048) {
+        // The windows [streams][n] are one channel of streams*n samples framed with hop n: frame f = stream f.  The
+        // fast path then packs streams 2k, 2k+1 into its shared sub-transforms (half the transform work of one
+        // frame per channel); outputs [1][streams][bars] and aux [1][streams] have the layout of [streams][1][..].
+        const long long S = (long long)s->streams * c.n;
+        rc = run_range(h, s->d_window, 1, S, 1, S, s->streams, 0, 0, s->streams, 0, s->streams, 0, s->streams, bars, bars_i32, true, nullptr, st,
+                       nullptr, false, c.n);
+    } else {
+        // one frame per stream: channels = streams, samples = n
+        rc = run_range(h, s->d_window, s->streams, c.n, 1, c.n, 1, 0, 0, 1, 0, 1, 0, 1, bars, bars_i32, true, nullptr, st, nullptr, true);
+    }
     if (rc) return rc;
     StreamBeatParams bp;
     bp.aux_w = h->d_aux;

@@ -397,7 +397,7 @@ __global__ void __launch_bounds__(RdifShape<N, F>::THREADS, MINB) stft_bars_rdif
     using Sh = RdifShape<N, F>;
     constexpr int M = Sh::M, SUBG = Sh::SUBG, SLOT = Sh::SLOT;
     constexpr int MAGS = Sh::mag_stride(ROWS);
-    static_assert(N == 4096 || N == 2048, "N = 16 M with M = 256 (two radix-16 sub-passes) or M = 128 (radix 16, then radix 8)");
+    static_assert(N == 4096 || N == 2048 || N == 1024, "N = 16 M with M = 256 (two radix-16 sub-passes), 128 (radix 16, radix 8) or 64 (radix 16, radix 4)");
     static_assert(F == 2 || F == 4, "frames are packed in pairs; the tail moves F floats as one vector");
     // HOPQ > 0: hop = HOPQ*M, the tile's frames share their samples (NX per column per tile).
     // HOPQ = 0: any hop; every frame loads its own 16 samples per column, one frame pair (32) at a time.
@@ -444,11 +444,12 @@ __global__ void __launch_bounds__(RdifShape<N, F>::THREADS, MINB) stft_bars_rdif
         if (M == 256) {
 #pragma unroll
             for (int r = 1; r < 16; r++) twc[r] = __ldg(p.twm + j * r);
-        } else { // M = 128: second sub-pass is two radix-8 butterflies per lane, jj = j + 8 tt: W_128^(jj r), r = 1..7
+        } else { // M = 128 / 64: second sub-pass is 16/R2 radix-R2 butterflies per lane (R2 = M/16), jj = j + SUBG tt: W_M^(jj r)
+            constexpr int R2 = M == 256 ? 8 : M / 16;
 #pragma unroll
-            for (int tt = 0; tt < 2; tt++)
+            for (int tt = 0; tt < 16 / R2; tt++)
 #pragma unroll
-                for (int r = 1; r < 8; r++) twc[8 * tt + r] = __ldg(p.twm + (((j + 8 * tt) * r) & (M - 1)));
+                for (int r = 1; r < R2; r++) twc[R2 * tt + r] = __ldg(p.twm + (((j + SUBG * tt) * r) & (M - 1)));
         }
     }
 
@@ -587,8 +588,11 @@ __global__ void __launch_bounds__(RdifShape<N, F>::THREADS, MINB) stft_bars_rdif
                 }
             }
         };
-        // M = 128 (N = 2048): 8 lanes per slot, radix 16 then two radix-8 butterflies per lane
-        auto pass_bc128 = [&](const int pr) {
+        // M = 128 / 64 (N = 2048 / 1024): SUBG = M/16 lanes per slot, radix 16, then NT = 16/R2 radix-R2 butterflies
+        // per lane with R2 = M/16 (8 or 4): butterfly jj = j + SUBG*tt reads X1[jj + 16 r] and leaves Z[jj + 16 kk]
+        auto pass_bc_small = [&](const int pr) {
+            constexpr int R2 = M == 256 ? 8 : M / 16, NT = 16 / R2, HALF = R2 / 2;
+            auto reg_of = [](int kk) { return R2 == 8 ? (((kk & 3) << 1) | (kk >> 2)) : kk; }; // Radix<R2>::out_index(reg_of(kk)) == kk
             float2* s = slots + (pr * 16 + hw) * SLOT;
             float2 v[16];
 #pragma unroll
@@ -599,72 +603,74 @@ __global__ void __launch_bounds__(RdifShape<N, F>::THREADS, MINB) stft_bars_rdif
             for (int rr = 0; rr < 16; rr++) s[pad_index(16 * j + Radix<16>::out_index(rr))] = v[rr];
             wsync();
 #pragma unroll
-            for (int tt = 0; tt < 2; tt++) {
+            for (int tt = 0; tt < NT; tt++) {
+                const int jj = j + SUBG * tt;
 #pragma unroll
-                for (int r = 0; r < 8; r++) v[8 * tt + r] = s[pad_index((j + 8 * tt) + 16 * r)];
+                for (int r = 0; r < R2; r++) v[R2 * tt + r] = s[pad_index(jj + 16 * r)];
 #pragma unroll
-                for (int r = 1; r < 8; r++) v[8 * tt + r] = cmul(v[8 * tt + r], RESIDENT ? twc[8 * tt + r] : ldg_pinned(p.twm + (((j + 8 * tt) * r) & (M - 1))));
-                Radix<8>::run(v + 8 * tt);
+                for (int r = 1; r < R2; r++) v[R2 * tt + r] = cmul(v[R2 * tt + r], RESIDENT ? twc[R2 * tt + r] : ldg_pinned(p.twm + ((jj * r) & (M - 1))));
+                Radix<R2>::run(v + R2 * tt);
             }
-            // v[8 tt + rr] = Z[m], m = jj + 16 kk, jj = j + 8 tt, kk = Radix<8>::out_index(rr); register of kk: ((kk&3)<<1)|(kk>>2)
+            // v[R2 tt + rr] = Z[m], m = jj + 16 kk, kk = Radix<R2>::out_index(rr)
             float2* mg2 = mags + pr * MAGS;
             if (hw >= 2) {
-                // regular slot: m < 64 directly (bin k0 + 16 m), m >= 64 through the conjugate mirror (16-k0) + 16 (127-m)
+                // regular slot: m < M/2 directly (bin k0 + 16 m), m >= M/2 through the conjugate mirror (16-k0) + 16 (M-1-m)
                 const int k0 = hw >> 1;
                 float* mg = reinterpret_cast<float*>(mg2) + (hw & 1);
 #pragma unroll
-                for (int tt = 0; tt < 2; tt++) {
-                    const int jj = j + 8 * tt;
+                for (int tt = 0; tt < NT; tt++) {
+                    const int jj = j + SUBG * tt;
                     float* lo_base = mg + 2 * (k0 + 17 * jj);
                     float* hi_base = mg + 2 * ((16 - k0) + 17 * (15 - jj));
 #pragma unroll
-                    for (int rr = 0; rr < 8; rr++) {
-                        const int kk = Radix<8>::out_index(rr);
-                        const int c = kk < 4 ? kk : 7 - kk;
+                    for (int rr = 0; rr < R2; rr++) {
+                        const int kk = Radix<R2>::out_index(rr);
+                        const int c = kk < HALF ? kk : R2 - 1 - kk;
                         if (c < ROWS) {
-                            const float2 z = v[8 * tt + rr];
+                            const float2 z = v[R2 * tt + rr];
                             const float mag = sqrtf(fmaf(z.x, z.x, z.y * z.y));
-                            if (kk < 4) lo_base[2 * 272 * c] = mag;
+                            if (kk < HALF) lo_base[2 * 272 * c] = mag;
                             else hi_base[2 * 272 * c] = mag;
                         }
                     }
                 }
             } else {
-                // packed slot (hw 0: residue 0, partner m' = 128-m; hw 1: residue 8, partner m' = 127-m): the partner of
-                // (jj, kk) is (15-jj, 7-kk) for hw 1 and (16-jj, 7-kk) for hw 0, i.e. the other tt of lane 7-j / 8-j;
-                // lane 0 of hw 0 is its own partner: (8, 7-kk) for jj = 8 and (0, (8-kk)&7) for jj = 0
-                const int src = hw ? (7 - j) : ((8 - j) & 7);
+                // packed slot (hw 0: residue 0, partner m' = M-m; hw 1: residue 8, partner m' = M-1-m): the partner of
+                // (jj, kk) is (15-jj, R2-1-kk) for hw 1 and (16-jj, R2-1-kk) for hw 0, i.e. butterfly NT-1-tt of lane
+                // SUBG-1-j / SUBG-j; lane 0 of hw 0 is its own partner: butterfly NT-tt for tt > 0 and (0, (R2-kk) mod R2)
+                constexpr unsigned MASK = SUBG >= 16 ? 0xffffffffu : ((1u << ((2 * SUBG) & 31)) - 1u); // the lanes of hw 0 and 1
+                const int src = hw ? (SUBG - 1 - j) : ((SUBG - j) & (SUBG - 1));
                 const bool self = (hw == 0) && (j == 0);
 #pragma unroll
-                for (int tt = 0; tt < 2; tt++) {
+                for (int tt = 0; tt < NT; tt++) {
 #pragma unroll
-                    for (int kk = 0; kk < (ROWS < 4 ? ROWS : 4); kk++) {
-                        const int rr = ((kk & 3) << 1) | (kk >> 2);
-                        const int kp = 7 - kk, rp = ((kp & 3) << 1) | (kp >> 2);
-                        float pr_ = __shfl_sync(0x0000ffffu, v[8 * (1 - tt) + rp].x, src, 8);
-                        float pi_ = __shfl_sync(0x0000ffffu, v[8 * (1 - tt) + rp].y, src, 8);
+                    for (int kk = 0; kk < (ROWS < HALF ? ROWS : HALF); kk++) {
+                        const int rr = reg_of(kk), rp = reg_of(R2 - 1 - kk);
+                        float pr_ = __shfl_sync(MASK, v[R2 * (NT - 1 - tt) + rp].x, src, SUBG);
+                        float pi_ = __shfl_sync(MASK, v[R2 * (NT - 1 - tt) + rp].y, src, SUBG);
                         if (self) {
-                            const int ks = (8 - kk) & 7, rs = ((ks & 3) << 1) | (ks >> 2);
-                            pr_ = tt ? v[8 + rp].x : v[rs].x;
-                            pi_ = tt ? v[8 + rp].y : v[rs].y;
+                            const int rs = reg_of((R2 - kk) & (R2 - 1));
+                            const float2 own = tt ? v[R2 * ((NT - tt) & (NT - 1)) + rp] : v[rs];
+                            pr_ = own.x;
+                            pi_ = own.y;
                         }
-                        const float2 z = v[8 * tt + rr];
+                        const float2 z = v[R2 * tt + rr];
                         float ar = z.x + pr_, ai = z.y - pi_; // 2 * Xa
                         float br = z.x - pr_, bi = z.y + pi_; // 2i * Xb
-                        const int bin = 16 * ((j + 8 * tt) + 16 * kk) + (hw ? 8 : 0);
+                        const int bin = 16 * ((j + SUBG * tt) + 16 * kk) + (hw ? 8 : 0);
                         mg2[pad_index(bin)] = make_float2(0.5f * sqrtf(fmaf(ar, ar, ai * ai)), 0.5f * sqrtf(fmaf(br, br, bi * bi)));
                     }
                 }
-                if (self && ROWS >= 4) {
-                    // m = 64 (bin N/2) is its own partner: Z[64] = Xa[N/2] + i Xb[N/2], both real; jj = 0, kk = 4
-                    const int rr = ((4 & 3) << 1) | (4 >> 2);
+                if (self && ROWS >= HALF) {
+                    // m = M/2 (bin N/2) is its own partner: Z[M/2] = Xa[N/2] + i Xb[N/2], both real; jj = 0, kk = HALF
+                    const int rr = reg_of(HALF);
                     mg2[pad_index(N / 2)] = make_float2(fabsf(v[rr].x), fabsf(v[rr].y));
                 }
             }
         };
         auto pass_bc = [&](const int pr) {
             if constexpr (M == 256) pass_bc256(pr);
-            else pass_bc128(pr);
+            else pass_bc_small(pr);
         };
         // Order of work and CTA barriers: pass B/C of a pair needs pass A of that pair from every thread.
         //   A(0) | A(1) | B/C(0) B/C(1) | tail      (F = 4)          A(0) | B/C(0) | tail      (F = 2)

@@ -419,12 +419,6 @@ __global__ void __launch_bounds__(RdifShape<N, F>::THREADS, MINB) stft_bars_rdif
     int* t_bar0 = reinterpret_cast<int*>(t_seg + p.nseg);           // [bars+1]
     float* t_inv = reinterpret_cast<float*>(t_bar0 + p.bars_n + 1); // [bars]
     float* t_sg = t_inv + p.bars_n;                                 // [(2w+1)^2]
-    for (int i = threadIdx.x; i < p.nseg; i += M) t_seg[i] = __ldg(p.seg_packed + i);
-    for (int i = threadIdx.x; i <= p.bars_n; i += M) t_bar0[i] = __ldg(p.bar_seg0 + i);
-    for (int i = threadIdx.x; i < p.bars_n; i += M) t_inv[i] = __ldg(p.bar_inv + i);
-    for (int i = threadIdx.x; i < (2 * p.sg_half + 1) * (2 * p.sg_half + 1); i += M) t_sg[i] = p.sg ? __ldg(p.sg + i) : 0.0f;
-    __syncthreads();
-
     const int t = threadIdx.x;
     const int B = p.bars_n;
     const int j = t & (SUBG - 1);  // lane within the sub-transform
@@ -452,6 +446,14 @@ __global__ void __launch_bounds__(RdifShape<N, F>::THREADS, MINB) stft_bars_rdif
                 for (int r = 1; r < R2; r++) twc[R2 * tt + r] = __ldg(p.twm + (((j + SUBG * tt) * r) & (M - 1)));
         }
     }
+
+    // the tail's tables (their loads overlap the per-thread constants above: a one-tile launch, i.e. a streaming
+    // tick, waits for all of these once)
+    for (int i = threadIdx.x; i < p.nseg; i += M) t_seg[i] = __ldg(p.seg_packed + i);
+    for (int i = threadIdx.x; i <= p.bars_n; i += M) t_bar0[i] = __ldg(p.bar_seg0 + i);
+    for (int i = threadIdx.x; i < p.bars_n; i += M) t_inv[i] = __ldg(p.bar_inv + i);
+    for (int i = threadIdx.x; i < (2 * p.sg_half + 1) * (2 * p.sg_half + 1); i += M) t_sg[i] = p.sg ? __ldg(p.sg + i) : 0.0f;
+    __syncthreads();
 
     TileCursor cur;
     cur.init(p, blockIdx.x, gridDim.x, F);

@@ -740,8 +740,20 @@ extern "C" int fftl_stft_run(fftl_stft* h, const int16_t* pcm, int32_t channels,
     static const int dbg_skip = getenv("FFTL_E2E_SKIP") ? atoi(getenv("FFTL_E2E_SKIP")) : 0; // developer knob: 1 = no H2D, 2 = no D2H
     int slot = 0;
     int64_t nchunks = 0;
-    for (int64_t a = warm; a < fe; a += chunk, slot ^= 1, nchunks++) {
-        int64_t b = a + chunk < fe ? a + chunk : fe; // compute frames [a,b)
+    // Chunk sizes ramp up at the start and down at the end (chunk/8, /4, /2, chunk ... chunk, half of what is left
+    // until chunk/8): the first upload and the last download are the only transfers nothing overlaps with.
+    static const bool ramp = !getenv("FFTL_CHUNK_NORAMP"); // developer A/B switch
+    const int64_t min_chunk = ((chunk / 8) + 1) & ~(int64_t)1;
+    int64_t step = 0;
+    for (int64_t a = warm; a < fe; a += step, slot ^= 1, nchunks++) {
+        step = chunk;
+        if (ramp && chunk >= 4096) {
+            if (nchunks < 3) step = (chunk >> (3 - nchunks)) & ~(int64_t)1;
+            const int64_t rem = fe - a;
+            if (rem < 2 * step && rem > min_chunk) step = ((rem / 2) + 1) & ~(int64_t)1; // the tail halves
+            if (step < 2) step = 2;
+        }
+        int64_t b = a + step < fe ? a + step : fe; // compute frames [a,b)
         int64_t ea = a > fb ? a : fb;                // emit frames [ea,b)
         int64_t ne = b > ea ? b - ea : 0;
         // chunks are even-sized, so b is even unless it is fe: then frame b (if it exists) is the

@@ -244,7 +244,7 @@ constexpr int HB_STRIDE = FFTL_BEAT_SAMPLES + 2;
 //         X_f[k] = X_{f-1}[k] + (ring_new - ring_old) * W256^((f mod 256) k)
 //     The block's first state X_{fs-1} is one fp32 FFT done by 16 lanes; the updates run in double (exact to
 //     ~1e-16 per step, so the error of every frame is that of the seed: one fp32 transform, as before),
-//     one thread per bin k <= 160;
+//     one thread per bin k <= 128 (bins 129..160 are mirrors: the ring is real);
 //   - the peak scan of a frame is split over 8 lanes (20 bins each), 24 frames at a time;
 //   - AddBeatSample's 160-frame running sum is a difference of integer prefix sums.
 __device__ __forceinline__ float f64_to_f32(double x)
@@ -304,6 +304,12 @@ __device__ __forceinline__ void beat_ring_steps(const double* delta, const doubl
         }
 #pragma unroll
         for (int i = 0; i < NF; i++) hb[i * hb_stride] = hv[i];
+        // the ring is real, so |X[256-k]| = |X[k]|: bins 129..160 are the mirror of 127..96 and are not updated
+        // separately (one warp less in these rounds)
+        if (k >= FFTL_TEMPO_RING - FFTL_BEAT_SAMPLES && k < FFTL_TEMPO_RING / 2) {
+#pragma unroll
+            for (int i = 0; i < NF; i++) hb[i * hb_stride + (FFTL_TEMPO_RING - 2 * k)] = hv[i];
+        }
     }
 }
 
@@ -394,7 +400,7 @@ __global__ void __launch_bounds__(BEAT_THREADS) beat_post_kernel(const BeatParam
 
     const int k = tid; // bin of this thread in the update rounds
     double xr = 0.0, xi = 0.0;
-    if (k <= FFTL_BEAT_SAMPLES) {
+    if (k <= FFTL_TEMPO_RING / 2) {
         const float2 x0 = s_fft[pad_index(k)];
         xr = (double)x0.x;
         xi = (double)x0.y;
@@ -402,7 +408,7 @@ __global__ void __launch_bounds__(BEAT_THREADS) beat_post_kernel(const BeatParam
     int tw_i = (int)(((fs & (FFTL_TEMPO_RING - 1)) * k) & (FFTL_TEMPO_RING - 1)); // (f mod 256) k mod 256, stepped by k per frame
     for (int fi0 = 0; fi0 < nfr; fi0 += BEAT_CH) {
         const bool emit_any = fs + fi0 + BEAT_CH > p.frame_emit; // block-uniform
-        if (k <= FFTL_BEAT_SAMPLES) {                           // bins 0..159 and the [160] the reference reads out of bounds
+        if (k <= FFTL_TEMPO_RING / 2) {                         // bins 0..128; 129..159 and the [160] the reference reads out of bounds are mirrors
             if (fi0 + BEAT_CH <= nfr) {
                 if (emit_any) {
 #pragma unroll 1

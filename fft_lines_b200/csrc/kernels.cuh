@@ -433,15 +433,16 @@ __global__ void __launch_bounds__(BEAT_THREADS) beat_post_kernel(const BeatParam
             const int* h = s_hb[fr_i];
             const int i0 = 20 * sub;
             unsigned bits = 0;
-            int prev = (i0 == 0) ? 0 : h[i0 - 1];
+            // dold of bin i is dnew of bin i-1 (0 in front of bin 0); one subtraction, two compares chained
+            // through a predicate and one predicated OR per bin
             int cur = h[i0];
+            int dold = (i0 == 0) ? 0 : wrap_sub(cur, h[i0 - 1]);
 #pragma unroll
             for (int q = 0; q < 20; q++) {
-                int nxt = h[i0 + q + 1];
-                int dold = (i0 + q == 0) ? 0 : wrap_sub(cur, prev);
-                int dnew = wrap_sub(nxt, cur);
-                if (dold >= 0 && dnew <= 0) bits |= 1u << q;
-                prev = cur;
+                const int nxt = h[i0 + q + 1];
+                const int dnew = wrap_sub(nxt, cur);
+                asm("{\n\t.reg .pred p;\n\tsetp.ge.s32 p, %1, 0;\n\tsetp.le.and.s32 p, %2, 0, p;\n\t@p or.b32 %0, %0, %3;\n\t}" : "+r"(bits) : "r"(dold), "r"(dnew), "r"(1u << q));
+                dold = dnew;
                 cur = nxt;
             }
             // peaks before this lane's range (lanes of a frame are consecutive lanes of the warp)

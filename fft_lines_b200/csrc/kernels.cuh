@@ -262,7 +262,7 @@ constexpr int BEAT_FB = 96;
 // different frames overlap: only the two fma chains are serial.
 template <bool EMIT, int NF>
 __device__ __forceinline__ void beat_ring_steps(const double* delta, const double2* twd, const int k, int& tw_i, double& xr, double& xi, int* hb,
-                                                const int hb_stride, const int strict)
+                                                int* hb_mirror, const int hb_stride, const int strict)
 {
     double d[NF];
     double2 w[NF];
@@ -306,9 +306,9 @@ __device__ __forceinline__ void beat_ring_steps(const double* delta, const doubl
         for (int i = 0; i < NF; i++) hb[i * hb_stride] = hv[i];
         // the ring is real, so |X[256-k]| = |X[k]|: bins 129..160 are the mirror of 127..96 and are not updated
         // separately (one warp less in these rounds)
-        if (k >= FFTL_TEMPO_RING - FFTL_BEAT_SAMPLES && k < FFTL_TEMPO_RING / 2) {
+        if (hb_mirror) { // warp-uniform: bins 96..127 are one warp
 #pragma unroll
-            for (int i = 0; i < NF; i++) hb[i * hb_stride + (FFTL_TEMPO_RING - 2 * k)] = hv[i];
+            for (int i = 0; i < NF; i++) hb_mirror[i * hb_stride] = hv[i];
         }
     }
 }
@@ -406,21 +406,22 @@ __global__ void __launch_bounds__(BEAT_THREADS) beat_post_kernel(const BeatParam
         xi = (double)x0.y;
     }
     int tw_i = (int)(((fs & (FFTL_TEMPO_RING - 1)) * k) & (FFTL_TEMPO_RING - 1)); // (f mod 256) k mod 256, stepped by k per frame
+    const bool mirror = k >= FFTL_TEMPO_RING - FFTL_BEAT_SAMPLES && k < FFTL_TEMPO_RING / 2; // bins 96..127 also stand for 160..129
     for (int fi0 = 0; fi0 < nfr; fi0 += BEAT_CH) {
         const bool emit_any = fs + fi0 + BEAT_CH > p.frame_emit; // block-uniform
         if (k <= FFTL_TEMPO_RING / 2) {                         // bins 0..128; 129..159 and the [160] the reference reads out of bounds are mirrors
             if (fi0 + BEAT_CH <= nfr) {
                 if (emit_any) {
 #pragma unroll 1
-                    for (int j = 0; j < BEAT_CH; j += 4) beat_ring_steps<true, 4>(s_delta + fi0 + j, s_twd, k, tw_i, xr, xi, &s_hb[j][k], BEAT_HBROW, p.strict);
+                    for (int j = 0; j < BEAT_CH; j += 4) beat_ring_steps<true, 4>(s_delta + fi0 + j, s_twd, k, tw_i, xr, xi, &s_hb[j][k], mirror ? &s_hb[j][FFTL_TEMPO_RING - k] : nullptr, BEAT_HBROW, p.strict);
                 } else {
 #pragma unroll 1
-                    for (int j = 0; j < BEAT_CH; j += 4) beat_ring_steps<false, 4>(s_delta + fi0 + j, s_twd, k, tw_i, xr, xi, &s_hb[j][k], BEAT_HBROW, p.strict);
+                    for (int j = 0; j < BEAT_CH; j += 4) beat_ring_steps<false, 4>(s_delta + fi0 + j, s_twd, k, tw_i, xr, xi, &s_hb[j][k], mirror ? &s_hb[j][FFTL_TEMPO_RING - k] : nullptr, BEAT_HBROW, p.strict);
                 }
             } else {
                 for (int j = 0; fi0 + j < nfr; j++) {
-                    if (emit_any) beat_ring_steps<true, 1>(s_delta + fi0 + j, s_twd, k, tw_i, xr, xi, &s_hb[j][k], BEAT_HBROW, p.strict);
-                    else beat_ring_steps<false, 1>(s_delta + fi0 + j, s_twd, k, tw_i, xr, xi, &s_hb[j][k], BEAT_HBROW, p.strict);
+                    if (emit_any) beat_ring_steps<true, 1>(s_delta + fi0 + j, s_twd, k, tw_i, xr, xi, &s_hb[j][k], mirror ? &s_hb[j][FFTL_TEMPO_RING - k] : nullptr, BEAT_HBROW, p.strict);
+                    else beat_ring_steps<false, 1>(s_delta + fi0 + j, s_twd, k, tw_i, xr, xi, &s_hb[j][k], mirror ? &s_hb[j][FFTL_TEMPO_RING - k] : nullptr, BEAT_HBROW, p.strict);
                 }
             }
         }

@@ -397,7 +397,8 @@ __global__ void __launch_bounds__(RdifShape<N, F>::THREADS, MINB) stft_bars_rdif
     using Sh = RdifShape<N, F>;
     constexpr int M = Sh::M, SUBG = Sh::SUBG, SLOT = Sh::SLOT;
     constexpr int MAGS = Sh::mag_stride(ROWS);
-    static_assert(N == 4096 || N == 2048 || N == 1024, "N = 16 M with M = 256 (two radix-16 sub-passes), 128 (radix 16, radix 8) or 64 (radix 16, radix 4)");
+    static_assert(N == 8192 || N == 4096 || N == 2048 || N == 1024,
+                  "N = 16 M with M = 512 (radix 16, 16, 2), 256 (radix 16, 16), 128 (radix 16, 8) or 64 (radix 16, 4)");
     static_assert(F == 2 || F == 4, "frames are packed in pairs; the tail moves F floats as one vector");
     // HOPQ > 0: hop = HOPQ*M, the tile's frames share their samples (NX per column per tile).
     // HOPQ = 0: any hop; every frame loads its own 16 samples per column, one frame pair (32) at a time.
@@ -438,8 +439,11 @@ __global__ void __launch_bounds__(RdifShape<N, F>::THREADS, MINB) stft_bars_rdif
         if (M == 256) {
 #pragma unroll
             for (int r = 1; r < 16; r++) twc[r] = __ldg(p.twm + j * r);
+        } else if (M == 512) { // second sub-pass of three: W_512^(2 k r), k = j mod 16
+#pragma unroll
+            for (int r = 1; r < 16; r++) twc[r] = __ldg(p.twm + ((2 * (j & 15) * r) & (M - 1)));
         } else { // M = 128 / 64: second sub-pass is 16/R2 radix-R2 butterflies per lane (R2 = M/16), jj = j + SUBG tt: W_M^(jj r)
-            constexpr int R2 = M == 256 ? 8 : M / 16;
+            constexpr int R2 = M >= 256 ? 8 : M / 16;
 #pragma unroll
             for (int tt = 0; tt < 16 / R2; tt++)
 #pragma unroll
@@ -593,7 +597,7 @@ __global__ void __launch_bounds__(RdifShape<N, F>::THREADS, MINB) stft_bars_rdif
         // M = 128 / 64 (N = 2048 / 1024): SUBG = M/16 lanes per slot, radix 16, then NT = 16/R2 radix-R2 butterflies
         // per lane with R2 = M/16 (8 or 4): butterfly jj = j + SUBG*tt reads X1[jj + 16 r] and leaves Z[jj + 16 kk]
         auto pass_bc_small = [&](const int pr) {
-            constexpr int R2 = M == 256 ? 8 : M / 16, NT = 16 / R2, HALF = R2 / 2;
+            constexpr int R2 = M >= 256 ? 8 : M / 16, NT = 16 / R2, HALF = R2 / 2; // (M >= 256: never called, placeholder)
             auto reg_of = [](int kk) { return R2 == 8 ? (((kk & 3) << 1) | (kk >> 2)) : kk; }; // Radix<R2>::out_index(reg_of(kk)) == kk
             float2* s = slots + (pr * 16 + hw) * SLOT;
             float2 v[16];
@@ -670,8 +674,78 @@ __global__ void __launch_bounds__(RdifShape<N, F>::THREADS, MINB) stft_bars_rdif
                 }
             }
         };
+        // M = 512 (N = 8192): one warp per slot, radix 16, radix 16, radix 2 (eight butterflies per lane); the last
+        // pass leaves Z[m], m = j + 32 tt + 256 rr, in v[2 tt + rr].  All sixteen 256-bin rows are kept.
+        auto pass_bc512 = [&](const int pr) {
+            float2* s = slots + (pr * 16 + hw) * SLOT;
+            float2 v[16];
+#pragma unroll
+            for (int r = 0; r < 16; r++) v[r] = s[pad_index(j + r * SUBG)];
+            radix16_fused<false>(v, nullptr);
+            wsync();
+#pragma unroll
+            for (int rr = 0; rr < 16; rr++) s[pad_index(16 * j + Radix<16>::out_index(rr))] = v[rr];
+            wsync();
+#pragma unroll
+            for (int r = 0; r < 16; r++) v[r] = s[pad_index(j + r * SUBG)];
+            if (!RESIDENT) {
+#pragma unroll
+                for (int r = 1; r < 16; r++) twc[r] = ldg_pinned(p.twm + ((2 * (j & 15) * r) & (M - 1)));
+            }
+            radix16_fused<true>(v, twc);
+            wsync();
+            {
+                const int k = j & 15, j0 = (j - k) * 16 + k;
+#pragma unroll
+                for (int rr = 0; rr < 16; rr++) s[pad_index(j0 + 16 * Radix<16>::out_index(rr))] = v[rr];
+            }
+            wsync();
+#pragma unroll
+            for (int tt = 0; tt < 8; tt++) {
+                const int jb = j + 32 * tt;
+                const float2 a = s[pad_index(jb)], b = cmul(s[pad_index(jb + 256)], __ldg(p.twm + jb));
+                v[2 * tt] = cadd(a, b);
+                v[2 * tt + 1] = csub(a, b);
+            }
+            float2* mg2 = mags + pr * MAGS;
+            if (hw >= 2) {
+                // regular slot: rr = 0 is bin k0 + 16 m (m < 256), rr = 1 the conjugate mirror (16-k0) + 16 (511-m)
+                const int k0 = hw >> 1;
+                float* mg = reinterpret_cast<float*>(mg2) + (hw & 1);
+#pragma unroll
+                for (int tt = 0; tt < 8; tt++) {
+                    const int m = j + 32 * tt;
+                    const float2 z0 = v[2 * tt], z1 = v[2 * tt + 1];
+                    mg[2 * (k0 + 17 * m)] = sqrtf(fmaf(z0.x, z0.x, z0.y * z0.y));
+                    mg[2 * ((16 - k0) + 17 * (255 - m))] = sqrtf(fmaf(z1.x, z1.x, z1.y * z1.y));
+                }
+            } else {
+                // packed slot (hw 0: residue 0, partner m' = 512-m; hw 1: residue 8, partner m' = 511-m); bins m < 256
+                // are rr = 0, their partners are rr = 1 of butterfly 7-tt in lane 31-j (hw 1) or 32-j (hw 0, j > 0);
+                // lane 0 of hw 0: butterfly 8-tt of its own for tt > 0, and m = 0 (DC) is its own partner
+                const int src = hw ? (31 - j) : ((32 - j) & 31);
+                const bool self = (hw == 0) && (j == 0);
+#pragma unroll
+                for (int tt = 0; tt < 8; tt++) {
+                    float pr_ = __shfl_sync(0xffffffffu, v[2 * (7 - tt) + 1].x, src);
+                    float pi_ = __shfl_sync(0xffffffffu, v[2 * (7 - tt) + 1].y, src);
+                    if (self) {
+                        const float2 own = tt ? v[2 * ((8 - tt) & 7) + 1] : v[0];
+                        pr_ = own.x;
+                        pi_ = own.y;
+                    }
+                    const float2 z = v[2 * tt];
+                    float ar = z.x + pr_, ai = z.y - pi_; // 2 * Xa
+                    float br = z.x - pr_, bi = z.y + pi_; // 2i * Xb
+                    const int bin = 16 * (j + 32 * tt) + (hw ? 8 : 0);
+                    mg2[pad_index(bin)] = make_float2(0.5f * sqrtf(fmaf(ar, ar, ai * ai)), 0.5f * sqrtf(fmaf(br, br, bi * bi)));
+                }
+                if (self) mg2[pad_index(N / 2)] = make_float2(fabsf(v[1].x), fabsf(v[1].y)); // m = 256: Xa[N/2] + i Xb[N/2], both real
+            }
+        };
         auto pass_bc = [&](const int pr) {
-            if constexpr (M == 256) pass_bc256(pr);
+            if constexpr (M == 512) pass_bc512(pr);
+            else if constexpr (M == 256) pass_bc256(pr);
             else pass_bc_small(pr);
         };
         // Order of work and CTA barriers: pass B/C of a pair needs pass A of that pair from every thread.

@@ -240,9 +240,9 @@ def test_fast_path_interleaved_pcm(oracle, lib, hop):
     assert (part["bars"] == planar["bars"][:, 101:250]).all()
 
 
-@pytest.mark.parametrize("n", [2048, 4096])
+@pytest.mark.parametrize("n", [1024, 2048, 4096, 8192])
 def test_fast_path_variants_both_sizes(oracle, lib, n):
-    """The real-input fast path at the reference's own N = 2048 (global.h:3) and at 4096: shared-sample variant
+    """The real-input fast path at the reference's own N = 2048 (global.h:3), at 4096 and at its other sizes: shared-sample variant
     (hop 512), own-sample variant (hop 300), windowed and not, one magnitude row and the full band including
     bin N/2, each against the oracle, against the generic kernel and shard == full."""
     import os
@@ -250,7 +250,7 @@ def test_fast_path_variants_both_sizes(oracle, lib, n):
     cfgs = [lib.extended_config(n, 512, 100),                       # Hann, log bins to 20 kHz, SG
             lib.extended_config(n, 512, 64, fmax=2000.0),           # few magnitude rows
             lib.extended_config(n, 300, 100, sg_half=0),            # own-sample variant, no smoothing
-            lib.reference_config(n, 512, n // 2 + 1),               # every bin including N/2 (bars = N/2 + 1)
+            lib.reference_config(n, 512, min(n // 2 + 1, 4096)),    # every bin including N/2 (bars = N/2 + 1, FFTL_MAX_BARS at most)
             lib.reference_config(n, 512, 100, circle=1)]
     for cfg in cfgs:
         got, _ = _check(oracle, lib, cfg, pcm)

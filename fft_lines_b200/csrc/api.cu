@@ -399,10 +399,10 @@ extern "C" int fftl_stft_create(const fftl_config* cfg, int device, fftl_stft** 
         for (int b = 0; b < B; b++) h->mag_bins = hi[b] > h->mag_bins ? hi[b] : h->mag_bins;
         // work list of the segment sums in bin order, packed for the fast kernel
         std::vector<int> packed(h->nseg);
-        h->seg_packable = h->nseg < (1 << 15);
+        h->seg_packable = h->nseg < (1 << 14);
         for (int i = 0; i < h->nseg; i++) {
             const int k = i, pl = pad_index(seg_lo[k]);
-            if (pl >= (1 << 13)) h->seg_packable = false;
+            if (pl >= (1 << 14)) h->seg_packable = false;
             packed[i] = FFTL_SEG_PACK(pl, seg_hi[k] - seg_lo[k], k);
         }
         H_TRY(cudaMalloc(&h->d_seg_packed, sizeof(int) * h->nseg));
@@ -483,13 +483,13 @@ extern "C" int64_t fftl_stft_launch_count(const fftl_stft* h) { return h ? h->la
 static cudaError_t try_rdif(const fftl_stft* h, const StftParams& q, int channels, long long samples, cudaStream_t st)
 {
     const fftl_config& c = h->cfg;
-    if (c.n != 8192 && c.n != 4096 && c.n != 2048 && c.n != 1024) return cudaErrorNotSupported;
+    if (c.n != 16384 && c.n != 8192 && c.n != 4096 && c.n != 2048 && c.n != 1024) return cudaErrorNotSupported;
     // hop = 1, 2 or 4 columns (n/16 samples) on planar PCM: the frames of a tile share their samples in registers;
     // any other hop, or interleaved PCM: the variant in which every frame loads its own (hopq = 0).
     // n = 2048 is built for hop 512 (4 columns) and the own-samples variant, n = 1024 for the own-samples variant.
     const int M = c.n / 16;
     int hopq = (q.hop % M) == 0 ? q.hop / M : 0; // q.hop: the caller's hop (the streaming front end passes n: one frame per window)
-    if ((hopq != 1 && hopq != 2 && hopq != 4) || q.sample_stride != 1 || (c.n == 2048 && hopq != 4) || c.n == 1024 || (c.n == 8192 && hopq != 1)) hopq = 0;
+    if ((hopq != 1 && hopq != 2 && hopq != 4) || q.sample_stride != 1 || (c.n == 2048 && hopq != 4) || c.n == 1024 || c.n == 16384 || (c.n == 8192 && hopq != 1)) hopq = 0;
     if (getenv("FFTL_DISABLE_RDIF") || !h->seg_packable) return cudaErrorNotSupported;
     RdifParams p;
     memset(&p, 0, sizeof(p));
@@ -524,8 +524,8 @@ static cudaError_t try_rdif(const fftl_stft* h, const StftParams& q, int channel
     const int full_rows = c.n / 512;
     p.mag_rows = (h->mag_bins + 255) / 256;       // bins < 256*rows are kept; all rows also keep bin N/2
     if (p.mag_rows > full_rows || h->mag_bins > c.n / 2) p.mag_rows = full_rows;
-    if (c.n == 8192) p.mag_rows = full_rows; // built with all rows only
-    p.mag_stride = c.n == 8192 ? RdifShape<8192, 4>::mag_stride(p.mag_rows) : c.n == 4096 ? RdifShape<4096, 4>::mag_stride(p.mag_rows) : c.n == 2048 ? RdifShape<2048, 4>::mag_stride(p.mag_rows) : RdifShape<1024, 4>::mag_stride(p.mag_rows);
+    if (c.n >= 8192) p.mag_rows = full_rows; // built with all rows only
+    p.mag_stride = c.n == 16384 ? RdifShape<16384, 2>::mag_stride(p.mag_rows) : c.n == 8192 ? RdifShape<8192, 4>::mag_stride(p.mag_rows) : c.n == 4096 ? RdifShape<4096, 4>::mag_stride(p.mag_rows) : c.n == 2048 ? RdifShape<2048, 4>::mag_stride(p.mag_rows) : RdifShape<1024, 4>::mag_stride(p.mag_rows);
     for (int i = 0; i < 4; i++) p.beat_bars[i] = q.beat_bars[i];
     p.zoom = q.zoom;
     p.circle_add = q.circle_add;
@@ -996,7 +996,7 @@ extern "C" int fftl_stream_push_device(fftl_stream* s, const int16_t* fresh, int
         stream_slide_kernel<<<s->streams, 256, 0, st>>>(s->d_window, fresh, c.n, count, stride, s->move_mode == FFTL_MOVE_REFERENCE);
     CUDA_TRY(cudaGetLastError());
     int rc;
-    if (c.n == 8192 || c.n == 4096 || c.n == 2048 || c.n == 1024) {
+    if (c.n == 16384 || c.n == 8192 || c.n == 4096 || c.n == 2048 || c.n == 1024) {
         // The windows [streams][n] are one channel of streams*n samples framed with hop n: frame f = stream f.  The
         // fast path then packs streams 2k, 2k+1 into its shared sub-transforms (half the transform work of one
         // frame per channel); outputs [1][streams][bars] and aux [1][streams] have the layout of [streams][1][..].

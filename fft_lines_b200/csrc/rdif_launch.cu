@@ -15,14 +15,15 @@ static cudaError_t launch_rdif(int num_sms, RdifParams p, int channels, cudaStre
 {
     // design points: N = 4096: two CTAs of 256 threads per SM (128 registers, <= 113 KB shared memory each);
     // N = 2048: four CTAs of 128 threads (three when the tables are large); N = 1024: eight CTAs of 64 threads;
-    // N = 8192: one CTA of 512 threads
-    constexpr int MINB = N == 8192 ? 1 : N == 4096 ? 2 : (N == 2048 ? 4 : 8);
+    // N = 8192 and 16384: one CTA of 512 threads
+    constexpr int MINB = N >= 8192 ? 1 : N == 4096 ? 2 : (N == 2048 ? 4 : 8);
+    constexpr bool RESIDENT = N != 16384; // two columns per thread at N = 16384: per-column constants are reloaded
     using Sh = RdifShape<N, F>;
     size_t smem = Sh::smem_bytes(p.bars_n, p.nseg, p.sg_half, ROWS);
     if ((smem + 1024) * (MINB <= 2 ? MINB : MINB - 1) > 228 * 1024) return cudaErrorNotSupported;
     if (!rdif_set_tiles(p, channels, F, HOPQ, N)) return cudaErrorNotSupported;
     if (p.total_tiles <= 0) return cudaSuccess;
-    auto kern = stft_bars_rdif_kernel<N, F, HOPQ, WIN, true, MINB, SGW, ROWS>;
+    auto kern = stft_bars_rdif_kernel<N, F, HOPQ, WIN, RESIDENT, MINB, SGW, ROWS>;
     cudaError_t e = cudaFuncSetAttribute(kern, cudaFuncAttributeMaxDynamicSharedMemorySize, (int)smem);
     if (e != cudaSuccess) return e;
     long long grid = (long long)MINB * num_sms;
@@ -56,6 +57,13 @@ static cudaError_t launch_rdif_8k(int num_sms, const RdifParams& p, int channels
     return launch_rdif<8192, 4, HOPQ, WIN, -1, 16>(num_sms, p, channels, st);
 }
 
+// N = 16384: one frame pair per tile, own samples, all thirty-two magnitude rows
+template <bool WIN>
+static cudaError_t launch_rdif_16k(int num_sms, const RdifParams& p, int channels, cudaStream_t st)
+{
+    return launch_rdif<16384, 2, 0, WIN, -1, 32>(num_sms, p, channels, st);
+}
+
 // N = 1024 (own-samples variant only: the many-stream front end and odd hops)
 template <bool WIN>
 static cudaError_t launch_rdif_1k(int num_sms, const RdifParams& p, int channels, cudaStream_t st)
@@ -82,6 +90,13 @@ static cudaError_t launch_rdif_sg(int num_sms, const RdifParams& p, int channels
 #define FFTL_CAT(a, b) FFTL_CAT2(a, b)
 cudaError_t FFTL_CAT(launch_rdif_h, FFTL_RDIF_HOPQ)(int n, bool win, int num_sms, const RdifParams& p, int channels, cudaStream_t st)
 {
+    if (n == 16384) {
+#if FFTL_RDIF_HOPQ == 0
+        return win ? launch_rdif_16k<true>(num_sms, p, channels, st) : launch_rdif_16k<false>(num_sms, p, channels, st);
+#else
+        return cudaErrorNotSupported;
+#endif
+    }
     if (n == 8192) {
 #if FFTL_RDIF_HOPQ == 0 || FFTL_RDIF_HOPQ == 1
         return win ? launch_rdif_8k<FFTL_RDIF_HOPQ, true>(num_sms, p, channels, st) : launch_rdif_8k<FFTL_RDIF_HOPQ, false>(num_sms, p, channels, st);

@@ -103,8 +103,9 @@ __device__ __forceinline__ void real_dft16(const float* x, const float* w, float
 
 template <int N, int F> struct RdifShape {
     static constexpr int M = N / 16;                 // sub-transform size and pass-A thread count
-    static constexpr int THREADS = M;                // one thread per column
-    static constexpr int SUBG = M / 16;              // lanes per sub-transform
+    static constexpr int THREADS = M > 512 ? 512 : M; // one thread per column; M = 1024: two columns per thread
+    static constexpr int COLS = M / THREADS;
+    static constexpr int SUBG = M / 16 > 32 ? 32 : M / 16; // lanes per sub-transform (a warp at most)
     static constexpr int SLOT = padded_size(M);      // float2 per slot
     static constexpr int SLOTS = 8 * F;              // per tile
     static constexpr int NB = N / 2 + 1;
@@ -236,10 +237,10 @@ struct TileCursor {
     __device__ __forceinline__ long long first_frame(const RdifParams& p, int F) const { return p.frame0 + (long long)tic * F; }
 };
 
-// Work-list entry of the segment sums: padded first bin (13 bits) | length 1..8 (4 bits) | segment number (15 bits).
+// Work-list entry of the segment sums: padded first bin (14 bits) | length 1..8 (4 bits) | segment number (14 bits).
 // The list stays in bin order: neighbouring lanes then read neighbouring magnitudes, which is conflict-free
 // (sorting it by length was measured: 5 % slower from bank conflicts).
-#define FFTL_SEG_PACK(padded_lo, cnt, idx) ((padded_lo) | ((cnt) << 13) | ((idx) << 17))
+#define FFTL_SEG_PACK(padded_lo, cnt, idx) ((padded_lo) | ((cnt) << 14) | ((idx) << 18))
 
 template <int F, int MAGS, int K> __device__ __forceinline__ void seg_steps(const float2* m0, int cnt, float* acc)
 {
@@ -265,8 +266,8 @@ __device__ __forceinline__ void rdif_segment_sums(const int* t_seg, const float2
     for (int base = 0; base < nseg; base += nthreads) {
         const int sgi = base + t;
         const int sd = sgi < nseg ? t_seg[sgi] : 0;
-        const int cnt = (sd >> 13) & 15;
-        const float2* m0 = mags + (sd & 0x1fff);
+        const int cnt = (sd >> 14) & 15;
+        const float2* m0 = mags + (sd & 0x3fff);
         float acc[F];
 #pragma unroll
         for (int f = 0; f < F; f++) acc[f] = 0.0f;
@@ -277,7 +278,7 @@ __device__ __forceinline__ void rdif_segment_sums(const int* t_seg, const float2
         if (__reduce_max_sync(0xffffffffu, cnt) <= 2) seg_steps<F, MAGS, 2>(m0, cnt, acc);
         else seg_steps<F, MAGS, 8>(m0, cnt, acc);
 #endif
-        if (cnt) FrameVec<F>::store(segsum + (sd >> 17) * F, acc);
+        if (cnt) FrameVec<F>::store(segsum + (int)((unsigned)sd >> 18) * F, acc);
     }
 }
 
@@ -395,10 +396,11 @@ template <int N, int F, int HOPQ, bool WINDOWED, bool RESIDENT, int MINB, int SG
 __global__ void __launch_bounds__(RdifShape<N, F>::THREADS, MINB) stft_bars_rdif_kernel(const RdifParams p)
 {
     using Sh = RdifShape<N, F>;
-    constexpr int M = Sh::M, SUBG = Sh::SUBG, SLOT = Sh::SLOT;
+    constexpr int M = Sh::M, SUBG = Sh::SUBG, SLOT = Sh::SLOT, THREADS = Sh::THREADS, COLS = Sh::COLS;
     constexpr int MAGS = Sh::mag_stride(ROWS);
-    static_assert(N == 8192 || N == 4096 || N == 2048 || N == 1024,
-                  "N = 16 M with M = 512 (radix 16, 16, 2), 256 (radix 16, 16), 128 (radix 16, 8) or 64 (radix 16, 4)");
+    static_assert(N == 16384 || N == 8192 || N == 4096 || N == 2048 || N == 1024,
+                  "N = 16 M with M = 1024 (radix 16, 16, 4), 512 (radix 16, 16, 2), 256 (radix 16, 16), 128 (radix 16, 8) or 64 (radix 16, 4)");
+    static_assert(COLS == 1 || (F == 2 && HOPQ == 0 && !RESIDENT), "M = 1024: one frame pair per tile, own samples, constants reloaded per column");
     static_assert(F == 2 || F == 4, "frames are packed in pairs; the tail moves F floats as one vector");
     // HOPQ > 0: hop = HOPQ*M, the tile's frames share their samples (NX per column per tile).
     // HOPQ = 0: any hop; every frame loads its own 16 samples per column, one frame pair (32) at a time.
@@ -453,10 +455,10 @@ __global__ void __launch_bounds__(RdifShape<N, F>::THREADS, MINB) stft_bars_rdif
 
     // the tail's tables (their loads overlap the per-thread constants above: a one-tile launch, i.e. a streaming
     // tick, waits for all of these once)
-    for (int i = threadIdx.x; i < p.nseg; i += M) t_seg[i] = __ldg(p.seg_packed + i);
-    for (int i = threadIdx.x; i <= p.bars_n; i += M) t_bar0[i] = __ldg(p.bar_seg0 + i);
-    for (int i = threadIdx.x; i < p.bars_n; i += M) t_inv[i] = __ldg(p.bar_inv + i);
-    for (int i = threadIdx.x; i < (2 * p.sg_half + 1) * (2 * p.sg_half + 1); i += M) t_sg[i] = p.sg ? __ldg(p.sg + i) : 0.0f;
+    for (int i = threadIdx.x; i < p.nseg; i += THREADS) t_seg[i] = __ldg(p.seg_packed + i);
+    for (int i = threadIdx.x; i <= p.bars_n; i += THREADS) t_bar0[i] = __ldg(p.bar_seg0 + i);
+    for (int i = threadIdx.x; i < p.bars_n; i += THREADS) t_inv[i] = __ldg(p.bar_inv + i);
+    for (int i = threadIdx.x; i < (2 * p.sg_half + 1) * (2 * p.sg_half + 1); i += THREADS) t_sg[i] = p.sg ? __ldg(p.sg + i) : 0.0f;
     __syncthreads();
 
     TileCursor cur;
@@ -483,7 +485,9 @@ __global__ void __launch_bounds__(RdifShape<N, F>::THREADS, MINB) stft_bars_rdif
                 }
             }
         };
-        if (HOPQ == 0) {
+        if (COLS > 1) {
+            // M = 1024: the samples are loaded column by column inside pass_a_cols
+        } else if (HOPQ == 0) {
             load_pair(0);
         } else if (all_samples) {
 #pragma unroll
@@ -496,7 +500,7 @@ __global__ void __launch_bounds__(RdifShape<N, F>::THREADS, MINB) stft_bars_rdif
         if (!late_alias) {
             __syncthreads(); // previous tile's tail is done with the aliased slots
         }
-        if (!RESIDENT) {
+        if (!RESIDENT && COLS == 1) {
             if (WINDOWED) {
 #pragma unroll
                 for (int q = 0; q < 16; q++) win[q] = ldg_pinned(p.window + t + M * q);
@@ -743,8 +747,146 @@ __global__ void __launch_bounds__(RdifShape<N, F>::THREADS, MINB) stft_bars_rdif
                 if (self) mg2[pad_index(N / 2)] = make_float2(fabsf(v[1].x), fabsf(v[1].y)); // m = 256: Xa[N/2] + i Xb[N/2], both real
             }
         };
+        // M = 1024 (N = 16384): pass A of the tile's only frame pair, one of this thread's COLS columns after the other;
+        // samples, window column and twiddles of a column are loaded when it is its turn
+        auto pass_a_cols = [&]() {
+#pragma unroll 1
+            for (int c = 0; c < COLS; c++) {
+                const int col = t + c * THREADS;
+                const int16_t* xc = cur.xp + (long long)col * p.sample_stride;
+                const long long qs = (long long)M * p.sample_stride;
+                float xs[32];
+#pragma unroll
+                for (int h = 0; h < 2; h++) {
+                    const long long off = (long long)h * p.hop;
+                    const int16_t* xf = xc + off * p.sample_stride;
+                    if (all_samples) {
+#pragma unroll
+                        for (int q = 0; q < 16; q++) xs[16 * h + q] = pcm_to_float(xf + q * qs);
+                    } else {
+                        const long long s0 = cur.first_frame(p, F) * (long long)p.hop + off + col;
+#pragma unroll
+                        for (int q = 0; q < 16; q++) xs[16 * h + q] = (s0 + (long long)q * M < p.samples) ? pcm_to_float(xf + q * qs) : 0.0f;
+                    }
+                }
+                float wn[16];
+                if (WINDOWED) {
+#pragma unroll
+                    for (int q = 0; q < 16; q++) wn[q] = __ldg(p.window + col + M * q);
+                }
+                float2 tc[9];
+#pragma unroll
+                for (int k0 = 1; k0 <= 8; k0++) tc[k0] = __ldg(p.tw + col * k0);
+                float2* ps = slots + pad_index(col);
+                float y0[2], y8[2];
+#pragma unroll
+                for (int h = 0; h < 2; h++) {
+                    float yr[9], yi[9];
+                    real_dft16<WINDOWED>(xs + 16 * h, wn, yr, yi);
+                    y0[h] = yr[0];
+                    y8[h] = yr[8];
+#pragma unroll
+                    for (int k0 = 1; k0 < 8; k0++) ps[(2 * k0 + h) * SLOT] = cmul(make_float2(yr[k0], yi[k0]), tc[k0]);
+                }
+                ps[0] = make_float2(y0[0], y0[1]);
+                ps[SLOT] = cmul(make_float2(y8[0], y8[1]), tc[8]);
+            }
+        };
+        // M = 1024: one warp per slot, 32 values per lane: radix 16 and radix 16 (two butterflies per lane each, jb = j + 32 u),
+        // then radix 4 (eight butterflies per lane, jb = j + 32 tt) leaving Z[m], m = j + 32 tt + 256 rr, in v[4 tt + rr].
+        // All thirty-two 256-bin rows are kept.
+        auto pass_bc1024 = [&](const int pr) {
+            float2* s = slots + (pr * 16 + hw) * SLOT;
+            float2 v[32];
+#pragma unroll
+            for (int u = 0; u < 2; u++)
+#pragma unroll
+                for (int r = 0; r < 16; r++) v[16 * u + r] = s[pad_index((j + 32 * u) + 64 * r)];
+            radix16_fused<false>(v, nullptr);
+            radix16_fused<false>(v + 16, nullptr);
+            wsync();
+#pragma unroll
+            for (int u = 0; u < 2; u++)
+#pragma unroll
+                for (int rr = 0; rr < 16; rr++) s[pad_index(16 * (j + 32 * u) + Radix<16>::out_index(rr))] = v[16 * u + rr];
+            wsync();
+#pragma unroll
+            for (int u = 0; u < 2; u++)
+#pragma unroll
+                for (int r = 0; r < 16; r++) v[16 * u + r] = s[pad_index((j + 32 * u) + 64 * r)];
+            {
+                // second sub-pass: W_1024^(4 k r), k = jb mod 16 = j mod 16 for both butterflies
+                float2 w2[16];
+#pragma unroll
+                for (int r = 1; r < 16; r++) w2[r] = __ldg(p.twm + ((4 * (j & 15) * r) & (M - 1)));
+                radix16_fused<true>(v, w2);
+                radix16_fused<true>(v + 16, w2);
+            }
+            wsync();
+#pragma unroll
+            for (int u = 0; u < 2; u++) {
+                const int jb = j + 32 * u, k = jb & 15, j0 = (jb - k) * 16 + k;
+#pragma unroll
+                for (int rr = 0; rr < 16; rr++) s[pad_index(j0 + 16 * Radix<16>::out_index(rr))] = v[16 * u + rr];
+            }
+            wsync();
+#pragma unroll
+            for (int tt = 0; tt < 8; tt++) {
+                const int jb = j + 32 * tt;
+                float2 a[4];
+                a[0] = s[pad_index(jb)];
+#pragma unroll
+                for (int r = 1; r < 4; r++) a[r] = cmul(s[pad_index(jb + 256 * r)], __ldg(p.twm + ((jb * r) & (M - 1))));
+                dft4(a[0], a[1], a[2], a[3]);
+#pragma unroll
+                for (int rr = 0; rr < 4; rr++) v[4 * tt + rr] = a[rr];
+            }
+            float2* mg2 = mags + pr * MAGS;
+            if (hw >= 2) {
+                // regular slot: rr = 0, 1 are bins k0 + 16 m (m < 512), rr = 2, 3 the conjugate mirror (16-k0) + 16 (1023-m)
+                const int k0 = hw >> 1;
+                float* mg = reinterpret_cast<float*>(mg2) + (hw & 1);
+#pragma unroll
+                for (int tt = 0; tt < 8; tt++) {
+#pragma unroll
+                    for (int rr = 0; rr < 4; rr++) {
+                        const int m = j + 32 * tt + 256 * rr;
+                        const float2 z = v[4 * tt + rr];
+                        const float mag = sqrtf(fmaf(z.x, z.x, z.y * z.y));
+                        if (rr < 2) mg[2 * (k0 + 17 * m)] = mag;
+                        else mg[2 * ((16 - k0) + 17 * (1023 - m))] = mag;
+                    }
+                }
+            } else {
+                // packed slot (hw 0: residue 0, partner m' = 1024-m; hw 1: residue 8, partner m' = 1023-m); bins m < 512 are
+                // rr = 0, 1, their partners rr' = 3-rr of butterfly 7-tt in lane 31-j (hw 1) or 32-j (hw 0, j > 0);
+                // lane 0 of hw 0: butterfly 8-tt of its own for tt > 0; tt = 0: m = 0 is its own partner, m = 256 pairs with 768
+                const int src = hw ? (31 - j) : ((32 - j) & 31);
+                const bool self = (hw == 0) && (j == 0);
+#pragma unroll
+                for (int tt = 0; tt < 8; tt++) {
+#pragma unroll
+                    for (int rr = 0; rr < 2; rr++) {
+                        float pr_ = __shfl_sync(0xffffffffu, v[4 * (7 - tt) + (3 - rr)].x, src);
+                        float pi_ = __shfl_sync(0xffffffffu, v[4 * (7 - tt) + (3 - rr)].y, src);
+                        if (self) {
+                            const float2 own = tt ? v[4 * ((8 - tt) & 7) + (3 - rr)] : (rr ? v[3] : v[0]);
+                            pr_ = own.x;
+                            pi_ = own.y;
+                        }
+                        const float2 z = v[4 * tt + rr];
+                        float ar = z.x + pr_, ai = z.y - pi_; // 2 * Xa
+                        float br = z.x - pr_, bi = z.y + pi_; // 2i * Xb
+                        const int bin = 16 * (j + 32 * tt + 256 * rr) + (hw ? 8 : 0);
+                        mg2[pad_index(bin)] = make_float2(0.5f * sqrtf(fmaf(ar, ar, ai * ai)), 0.5f * sqrtf(fmaf(br, br, bi * bi)));
+                    }
+                }
+                if (self) mg2[pad_index(N / 2)] = make_float2(fabsf(v[2].x), fabsf(v[2].y)); // m = 512: Xa[N/2] + i Xb[N/2], both real
+            }
+        };
         auto pass_bc = [&](const int pr) {
-            if constexpr (M == 512) pass_bc512(pr);
+            if constexpr (M == 1024) pass_bc1024(pr);
+            else if constexpr (M == 512) pass_bc512(pr);
             else if constexpr (M == 256) pass_bc256(pr);
             else pass_bc_small(pr);
         };
@@ -753,7 +895,8 @@ __global__ void __launch_bounds__(RdifShape<N, F>::THREADS, MINB) stft_bars_rdif
         // The barrier after A(0) is the one that lets the previous tile's tail finish with the buffers it
         // aliases onto the last pair's slots (late_alias).  (Running B/C(0) right behind A(1), with the second
         // barrier after it, was measured: 1.3 % slower with the tail's seven magnitude rows, equal without.)
-        pass_a(0);
+        if constexpr (COLS > 1) pass_a_cols();
+        else pass_a(0);
         if (HOPQ == 0 && F == 4) load_pair(1); // in flight across the barrier
         __syncthreads();
         if (F == 4) {
@@ -766,9 +909,9 @@ __global__ void __launch_bounds__(RdifShape<N, F>::THREADS, MINB) stft_bars_rdif
         }
         __syncthreads();
         // ================= bins -> bars, SG, outputs: every item carries the tile's F frames =================
-        rdif_segment_sums<F, MAGS>(t_seg, mags, segsum, p.nseg, t, M);
+        rdif_segment_sums<F, MAGS>(t_seg, mags, segsum, p.nseg, t, THREADS);
         __syncthreads();
-        for (int b = t; b < B; b += M) {
+        for (int b = t; b < B; b += THREADS) {
             const int a = t_bar0[b], e = t_bar0[b + 1];
             float acc[F];
             FrameVec<F>::load(segsum + a * F, acc);
@@ -786,7 +929,7 @@ __global__ void __launch_bounds__(RdifShape<N, F>::THREADS, MINB) stft_bars_rdif
         __syncthreads();
         // band energy / bass first (16 lanes of warp 0; the magnitudes are still in place), then the heights
         if (t < 4 * F) rdif_emit_beat<F, SGW>(p, raw, t_sg, mags, MAGS, t, cur.ch, cur.first_frame(p, F));
-        rdif_emit_bars<F, SGW>(p, raw, t_sg, t, M, cur.tic >= p.tic_emit_lo && cur.tic < p.tic_emit_hi, cur.o0, cur.first_frame(p, F));
+        rdif_emit_bars<F, SGW>(p, raw, t_sg, t, THREADS, cur.tic >= p.tic_emit_lo && cur.tic < p.tic_emit_hi, cur.o0, cur.first_frame(p, F));
         // No barrier here: the next tile's pass A starts at once; the barrier that protects the aliased
         // buffers is the one inside (late_alias) or in front of (otherwise) its pass A.
     }

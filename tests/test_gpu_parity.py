@@ -240,7 +240,7 @@ def test_fast_path_interleaved_pcm(oracle, lib, hop):
     assert (part["bars"] == planar["bars"][:, 101:250]).all()
 
 
-@pytest.mark.parametrize("n", [1024, 2048, 4096, 8192])
+@pytest.mark.parametrize("n", [1024, 2048, 4096, 8192, 16384])
 def test_fast_path_variants_both_sizes(oracle, lib, n):
     """The real-input fast path at the reference's own N = 2048 (global.h:3), at 4096 and at its other sizes: shared-sample variant
     (hop 512), own-sample variant (hop 300), windowed and not, one magnitude row and the full band including

@@ -119,7 +119,7 @@ for hop in (512, 4096):
     with F.BatchedSpectrum(F.extended_config(16384, hop, 512)) as sp:
         frames, ms, bms = timed_device(sp, pcm, reps=5)
     out.append({"config": "c4: 16384-pt Hann, hop %d, 512 log bars + SG + beat, 60 s stereo" % hop, "frames": frames, "ms": ms,
-                "bars_kernel_ms": bms, "frames_per_s": frames / ms * 1e3, "kernel": "stft_bars_kernel<16384> (generic)",
+                "bars_kernel_ms": bms, "frames_per_s": frames / ms * 1e3, "kernel": "stft_bars_rdif_kernel<16384> (fast path, own-samples variant)",
                 "roofline_frac_nominal_fp32": (frames / (bms * 1e-3)) * 5 * 16384 * 14 / 74.45e12})
 
 # ---- c5-style: 8 channels, chunked hours generated on the device and processed chunk by chunk (nothing is resident

@@ -146,6 +146,17 @@ __device__ __forceinline__ float pcm_to_float(const int16_t* p)
 #endif
 }
 
+// cos / sin of q*pi/8, q = 0..15 (the Hann column of column t is 0.5 - 0.5*cos(theta_t + q*pi/8))
+__device__ __forceinline__ constexpr float cos_pi8(int q)
+{
+    constexpr float c[16] = {1.0f, 0.92387953251128675613f, 0.70710678118654752440f, 0.38268343236508977173f,
+                             0.0f, -0.38268343236508977173f, -0.70710678118654752440f, -0.92387953251128675613f,
+                             -1.0f, -0.92387953251128675613f, -0.70710678118654752440f, -0.38268343236508977173f,
+                             0.0f, 0.38268343236508977173f, 0.70710678118654752440f, 0.92387953251128675613f};
+    return c[q];
+}
+__device__ __forceinline__ constexpr float sin_pi8(int q) { return cos_pi8((q + 12) & 15); } // sin(x) = cos(x - pi/2)
+
 // F floats per tail item, moved as one vector
 template <int F> struct FrameVec;
 template <> struct FrameVec<2> {
@@ -770,13 +781,16 @@ __global__ void __launch_bounds__(RdifShape<N, F>::THREADS, MINB) stft_bars_rdif
                     }
                 }
                 float wn[16];
+                float2 tc[9];
+                // one load per column: W_N^col = (cos th, -sin th); its powers by multiplication, the periodic Hann
+                // column 0.5 - 0.5 cos(th + q pi/8) from the angle-sum identity
+                tc[1] = __ldg(p.tw + col);
+#pragma unroll
+                for (int k0 = 2; k0 <= 8; k0++) tc[k0] = cmul(tc[k0 - 1], tc[1]);
                 if (WINDOWED) {
 #pragma unroll
-                    for (int q = 0; q < 16; q++) wn[q] = __ldg(p.window + col + M * q);
+                    for (int q = 0; q < 16; q++) wn[q] = fmaf(-0.5f * cos_pi8(q), tc[1].x, fmaf(-0.5f * sin_pi8(q), tc[1].y, 0.5f));
                 }
-                float2 tc[9];
-#pragma unroll
-                for (int k0 = 1; k0 <= 8; k0++) tc[k0] = __ldg(p.tw + col * k0);
                 float2* ps = slots + pad_index(col);
                 float y0[2], y8[2];
 #pragma unroll

@@ -760,7 +760,55 @@ __global__ void __launch_bounds__(RdifShape<N, F>::THREADS, MINB) stft_bars_rdif
         };
         // M = 1024 (N = 16384): pass A of the tile's only frame pair, one of this thread's COLS columns after the other;
         // samples, window column and twiddles of a column are loaded when it is its turn
+        // one column's share of pass A: x0 / x1 = the column's 16 samples of frame 0 / frame 1 of the pair
+        auto pass_a_col = [&](const int col, const float* x0, const float* x1) {
+            float wn[16];
+            float2 tc[9];
+            // one load per column: W_N^col = (cos th, -sin th); its powers by multiplication, the periodic Hann
+            // column 0.5 - 0.5 cos(th + q pi/8) from the angle-sum identity
+            tc[1] = __ldg(p.tw + col);
+#pragma unroll
+            for (int k0 = 2; k0 <= 8; k0++) tc[k0] = cmul(tc[k0 - 1], tc[1]);
+            if (WINDOWED) {
+#pragma unroll
+                for (int q = 0; q < 16; q++) wn[q] = fmaf(-0.5f * cos_pi8(q), tc[1].x, fmaf(-0.5f * sin_pi8(q), tc[1].y, 0.5f));
+            }
+            float2* ps = slots + pad_index(col);
+            float y0[2], y8[2];
+#pragma unroll
+            for (int h = 0; h < 2; h++) {
+                float yr[9], yi[9];
+                real_dft16<WINDOWED>(h ? x1 : x0, wn, yr, yi);
+                y0[h] = yr[0];
+                y8[h] = yr[8];
+#pragma unroll
+                for (int k0 = 1; k0 < 8; k0++) ps[(2 * k0 + h) * SLOT] = cmul(make_float2(yr[k0], yi[k0]), tc[k0]);
+            }
+            ps[0] = make_float2(y0[0], y0[1]);
+            ps[SLOT] = cmul(make_float2(y8[0], y8[1]), tc[8]);
+        };
         auto pass_a_cols = [&]() {
+            if (COLS == 2 && p.hop * 2 == M && p.sample_stride == 1) {
+                // hop = M/2 (configs[3]: 16384 / 512): frame 1 of column t is frame 0 of column t + M/2, and frame 1 of
+                // column t + M/2 is frame 0 of column t one row further on: 33 samples serve both columns and both frames
+                const int16_t* xc = cur.xp + t;
+                float xa[17], xb[16]; // x[t + M q], q = 0..16 and x[t + M/2 + M q], q = 0..15
+                if (all_samples) {
+#pragma unroll
+                    for (int q = 0; q < 17; q++) xa[q] = pcm_to_float(xc + q * M);
+#pragma unroll
+                    for (int q = 0; q < 16; q++) xb[q] = pcm_to_float(xc + M / 2 + q * M);
+                } else {
+                    const long long s0 = cur.first_frame(p, F) * (long long)p.hop + t;
+#pragma unroll
+                    for (int q = 0; q < 17; q++) xa[q] = (s0 + (long long)q * M < p.samples) ? pcm_to_float(xc + q * M) : 0.0f;
+#pragma unroll
+                    for (int q = 0; q < 16; q++) xb[q] = (s0 + M / 2 + (long long)q * M < p.samples) ? pcm_to_float(xc + M / 2 + q * M) : 0.0f;
+                }
+                pass_a_col(t, xa, xb);
+                pass_a_col(t + THREADS, xb, xa + 1);
+                return;
+            }
 #pragma unroll 1
             for (int c = 0; c < COLS; c++) {
                 const int col = t + c * THREADS;
@@ -780,30 +828,7 @@ __global__ void __launch_bounds__(RdifShape<N, F>::THREADS, MINB) stft_bars_rdif
                         for (int q = 0; q < 16; q++) xs[16 * h + q] = (s0 + (long long)q * M < p.samples) ? pcm_to_float(xf + q * qs) : 0.0f;
                     }
                 }
-                float wn[16];
-                float2 tc[9];
-                // one load per column: W_N^col = (cos th, -sin th); its powers by multiplication, the periodic Hann
-                // column 0.5 - 0.5 cos(th + q pi/8) from the angle-sum identity
-                tc[1] = __ldg(p.tw + col);
-#pragma unroll
-                for (int k0 = 2; k0 <= 8; k0++) tc[k0] = cmul(tc[k0 - 1], tc[1]);
-                if (WINDOWED) {
-#pragma unroll
-                    for (int q = 0; q < 16; q++) wn[q] = fmaf(-0.5f * cos_pi8(q), tc[1].x, fmaf(-0.5f * sin_pi8(q), tc[1].y, 0.5f));
-                }
-                float2* ps = slots + pad_index(col);
-                float y0[2], y8[2];
-#pragma unroll
-                for (int h = 0; h < 2; h++) {
-                    float yr[9], yi[9];
-                    real_dft16<WINDOWED>(xs + 16 * h, wn, yr, yi);
-                    y0[h] = yr[0];
-                    y8[h] = yr[8];
-#pragma unroll
-                    for (int k0 = 1; k0 < 8; k0++) ps[(2 * k0 + h) * SLOT] = cmul(make_float2(yr[k0], yi[k0]), tc[k0]);
-                }
-                ps[0] = make_float2(y0[0], y0[1]);
-                ps[SLOT] = cmul(make_float2(y8[0], y8[1]), tc[8]);
+                pass_a_col(col, xs, xs + 16);
             }
         };
         // M = 1024: one warp per slot, 32 values per lane: radix 16 and radix 16 (two butterflies per lane each, jb = j + 32 u),

@@ -270,7 +270,7 @@ def test_fast_path_variants_both_sizes(oracle, lib, n):
         assert (np.abs(gen["bars"] - got["bars"]) <= 1e-5 * fmax).all()
 
 
-@pytest.mark.parametrize("n,hop", [(4096, 512), (2048, 512), (4096, 480)])
+@pytest.mark.parametrize("n,hop", [(4096, 512), (2048, 512), (4096, 480), (1024, 480), (8192, 512), (16384, 512), (16384, 700)])
 def test_fast_path_many_channels_few_frames(oracle, lib, n, hop):
     """More CTAs than a channel has tiles: the persistent kernel's tile cursor steps over several channels at once,
     and the last tile of every channel is ragged (9 frames = 2 tiles + 1 frame)."""

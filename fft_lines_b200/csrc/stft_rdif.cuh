@@ -869,13 +869,20 @@ __global__ void __launch_bounds__(RdifShape<N, F>::THREADS, MINB) stft_bars_rdif
                 for (int rr = 0; rr < 16; rr++) s[pad_index(j0 + 16 * Radix<16>::out_index(rr))] = v[16 * u + rr];
             }
             wsync();
+            const float2 wj = __ldg(p.twm + j); // W_1024^j; W_1024^(j + 32 tt) = wj * W_32^tt
 #pragma unroll
             for (int tt = 0; tt < 8; tt++) {
                 const int jb = j + 32 * tt;
+                // W_32^tt = exp(-2 pi i tt / 32), tt = 0..7
+                constexpr float C32[8] = {1.0f, 0.98078528040323044913f, 0.92387953251128675613f, 0.83146961230254523708f,
+                                          0.70710678118654752440f, 0.55557023301960222474f, 0.38268343236508977173f, 0.19509032201612826785f};
+                const float2 w1 = tt ? cmul(wj, make_float2(C32[tt], -C32[8 - tt])) : wj; // sin(2 pi tt/32) = cos(2 pi (8-tt)/32)
+                const float2 w2 = cmul(w1, w1), w3 = cmul(w2, w1);
                 float2 a[4];
                 a[0] = s[pad_index(jb)];
-#pragma unroll
-                for (int r = 1; r < 4; r++) a[r] = cmul(s[pad_index(jb + 256 * r)], __ldg(p.twm + ((jb * r) & (M - 1))));
+                a[1] = cmul(s[pad_index(jb + 256)], w1);
+                a[2] = cmul(s[pad_index(jb + 512)], w2);
+                a[3] = cmul(s[pad_index(jb + 768)], w3);
                 dft4(a[0], a[1], a[2], a[3]);
 #pragma unroll
                 for (int rr = 0; rr < 4; rr++) v[4 * tt + rr] = a[rr];

@@ -282,6 +282,7 @@ struct fftl_stft {
     int mag_bins;                   // highest bin any bar (or the bass bin) reads, + 1
     int num_sms;
     int64_t fast_launches;
+    int kernel_select;              // FFTL_KERNEL_AUTO / FFTL_KERNEL_GENERIC (fftl_stft_set_kernel)
     int* d_aux;                     // [2][channels][nf_aux] (w then bass)
     size_t aux_capacity;            // ints
     int64_t launches;
@@ -424,6 +425,9 @@ extern "C" int fftl_stft_create(const fftl_config* cfg, int device, fftl_stft** 
         H_TRY(cudaEventCreateWithFlags(&h->ev_comp[i], cudaEventDisableTiming));
         H_TRY(cudaEventCreateWithFlags(&h->ev_d2h[i], cudaEventDisableTiming));
     }
+    // The uploads above are pageable-memory copies and memsets on the legacy stream; the handle's own streams are
+    // non-blocking and do not order against it, so the tables must have landed before the handle is handed out.
+    H_TRY(cudaDeviceSynchronize());
 #undef H_TRY
     *out = h;
     return FFTL_OK;
@@ -479,6 +483,15 @@ extern "C" int64_t fftl_stft_first_frame_needed(int64_t frame_begin, int32_t wit
 }
 
 extern "C" int64_t fftl_stft_launch_count(const fftl_stft* h) { return h ? h->launches : 0; }
+extern "C" int64_t fftl_stft_fast_launch_count(const fftl_stft* h) { return h ? h->fast_launches : 0; }
+
+extern "C" int fftl_stft_set_kernel(fftl_stft* h, int32_t which)
+{
+    if (!h) return set_error(FFTL_ERR_ARG, "handle is NULL");
+    if (which != FFTL_KERNEL_AUTO && which != FFTL_KERNEL_GENERIC) return set_error(FFTL_ERR_ARG, "unknown kernel selection %d", which);
+    h->kernel_select = which;
+    return FFTL_OK;
+}
 
 static cudaError_t try_rdif(const fftl_stft* h, const StftParams& q, int channels, long long samples, cudaStream_t st)
 {
@@ -490,7 +503,7 @@ static cudaError_t try_rdif(const fftl_stft* h, const StftParams& q, int channel
     const int M = c.n / 16;
     int hopq = (q.hop % M) == 0 ? q.hop / M : 0; // q.hop: the caller's hop (the streaming front end passes n: one frame per window)
     if ((hopq != 1 && hopq != 2 && hopq != 4) || q.sample_stride != 1 || (c.n == 2048 && hopq != 4) || c.n == 1024 || c.n == 16384 || (c.n == 8192 && hopq != 1)) hopq = 0;
-    if (getenv("FFTL_DISABLE_RDIF") || !h->seg_packable) return cudaErrorNotSupported;
+    if (h->kernel_select == FFTL_KERNEL_GENERIC || !h->seg_packable) return cudaErrorNotSupported;
     RdifParams p;
     memset(&p, 0, sizeof(p));
     p.pcm = q.pcm;
@@ -500,7 +513,6 @@ static cudaError_t try_rdif(const fftl_stft* h, const StftParams& q, int channel
     p.frame0 = q.frame0;
     p.frame_emit = q.frame_emit;
     p.frame_end = q.frame_end;
-    p.frames_total = q.frames_total;
     p.nf_emit = q.nf_emit;
     p.nf_aux = q.nf_aux;
     p.aux_base = q.aux_base;
@@ -541,7 +553,7 @@ static cudaError_t try_rdif(const fftl_stft* h, const StftParams& q, int channel
 // Core: frames [fb, fe) of every channel; aux (w, bass) indexed from aux_base
 // with per-channel stride nf_aux.  `compute_from` <= fb is where this call
 // starts computing aux (frames before it must already be in the aux arrays).
-static int run_range(fftl_stft* h, const int16_t* pcm, int channels, int64_t cstride, int64_t sstride, int64_t samples, int64_t frames_total, int64_t compute_from,
+static int run_range(fftl_stft* h, const int16_t* pcm, int channels, int64_t cstride, int64_t sstride, int64_t samples, int64_t compute_from,
                      int64_t fb, int64_t fe, int64_t out_base, int64_t nf_emit, int64_t aux_base, int64_t nf_aux, float* bars,
                      int32_t* bars_i32, bool aux, fftl_beat* beat, cudaStream_t st, cudaEvent_t* evs, bool force_generic = false, int hop_override = 0)
 {
@@ -554,7 +566,7 @@ static int run_range(fftl_stft* h, const int16_t* pcm, int channels, int64_t cst
     p.frame0 = compute_from;
     p.frame_emit = fb;
     p.frame_end = fe;
-    p.frames_total = frames_total;
+    p.samples = samples;
     p.nf_emit = nf_emit;
     p.nf_aux = nf_aux;
     p.aux_base = aux_base;
@@ -562,6 +574,7 @@ static int run_range(fftl_stft* h, const int16_t* pcm, int channels, int64_t cst
     p.tw = h->d_tw;
     p.lo = h->d_lo;
     p.hi = h->d_hi;
+    p.bar_inv = h->d_bar_inv;
     p.sg = h->d_sg;
     // outputs are addressed relative to frame_emit inside the kernel
     p.bars = bars + (fb - out_base) * (int64_t)c.bars;
@@ -630,24 +643,23 @@ static int check_run_args(fftl_stft* h, const void* pcm, int channels, int64_t s
     return FFTL_OK;
 }
 
-extern "C" int fftl_stft_run_device(fftl_stft* h, const int16_t* pcm, int32_t channels, int64_t samples, int64_t cstride,
-                                    int64_t sstride, int64_t fb, int64_t fe, float* bars, int32_t* bars_i32, fftl_beat* beat,
-                                    void* cuda_stream)
+// Shared body of the device-buffer entry points.  `pcm` is addressed with ABSOLUTE sample indices of the job
+// (a span-only shard passes a rebased pointer); samples at or beyond `samples_held` read as zero.
+static int run_device_impl(fftl_stft* h, const int16_t* pcm, int32_t channels, int64_t samples_held, int64_t cstride, int64_t sstride,
+                           int64_t fb, int64_t fe, float* bars, int32_t* bars_i32, fftl_beat* beat, cudaStream_t st)
 {
-    int rc = check_run_args(h, pcm, channels, samples, fb, fe, bars);
-    if (rc) return rc;
-    if (fe == fb) return FFTL_OK;
     CUDA_TRY(cudaSetDevice(h->device));
-    cudaStream_t st = (cudaStream_t)cuda_stream; // NULL = CUDA's default stream, as everywhere in CUDA
     int64_t warm = fb;
     if (beat) {
         warm = beat_warm_start(fb);
     }
     warm &= ~(int64_t)1; // frame f always shares its transform with frame f^1: results do not depend on the shard start
     int64_t nf_aux = fe - warm;
+    int rc;
     if (beat) {
         size_t need = sizeof(int) * 2 * (size_t)channels * (size_t)nf_aux;
         if (h->aux_capacity < need) {
+            // one call per handle may be in flight (fftlines.h): nothing else can be using the old buffer once st has drained
             CUDA_TRY(cudaStreamSynchronize(st));
             void* pv = h->d_aux;
             rc = ensure_bytes(&pv, &h->aux_capacity, need);
@@ -662,13 +674,63 @@ extern "C" int fftl_stft_run_device(fftl_stft* h, const int16_t* pcm, int32_t ch
         cap = cudaStreamCaptureStatusNone;
     }
     cudaEvent_t* evs = (cap == cudaStreamCaptureStatusNone) ? h->ev[h->timing_next] : nullptr;
-    rc = run_range(h, pcm, channels, cstride, sstride, samples, fftl_stft_num_frames(h, samples), warm, fb, fe, fb, fe - fb, warm, nf_aux, bars, bars_i32, beat != nullptr, beat, st, evs);
+    rc = run_range(h, pcm, channels, cstride, sstride, samples_held, warm, fb, fe, fb, fe - fb, warm, nf_aux, bars, bars_i32, beat != nullptr, beat, st, evs);
     if (rc) return rc;
     if (evs) {
         h->timing_next = (h->timing_next + 1) % TIMING_SLOTS;
         if (h->timing_count < TIMING_SLOTS) h->timing_count++;
     }
     return FFTL_OK;
+}
+
+extern "C" int fftl_stft_run_device(fftl_stft* h, const int16_t* pcm, int32_t channels, int64_t samples, int64_t cstride,
+                                    int64_t sstride, int64_t fb, int64_t fe, float* bars, int32_t* bars_i32, fftl_beat* beat,
+                                    void* cuda_stream)
+{
+    int rc = check_run_args(h, pcm, channels, samples, fb, fe, bars);
+    if (rc) return rc;
+    if (fe == fb) return FFTL_OK;
+    // NULL = CUDA's default stream, as everywhere in CUDA
+    return run_device_impl(h, pcm, channels, samples, cstride, sstride, fb, fe, bars, bars_i32, beat, (cudaStream_t)cuda_stream);
+}
+
+// Samples [*first, *end) of every channel that a run over frames [fb, fe) of a job of `total` samples reads:
+// from the first frame of the beat warm-up (rounded down to even) to the end of frame fe-1 or, when that frame
+// is even, of its pair partner fe (the two share packed sub-transforms), clipped to the job.
+extern "C" int fftl_stft_sample_span(const fftl_stft* h, int64_t total, int64_t fb, int64_t fe, int32_t with_beat, int64_t* first,
+                                     int64_t* end)
+{
+    if (!h || !first || !end) return set_error(FFTL_ERR_ARG, "NULL argument");
+    const int64_t F = fftl_stft_num_frames(h, total);
+    if (fb < 0 || fe < fb || fe > F) return set_error(FFTL_ERR_ARG, "frame range [%lld,%lld) outside [0,%lld]", (long long)fb, (long long)fe, (long long)F);
+    if (fe == fb) {
+        *first = *end = 0;
+        return FFTL_OK;
+    }
+    *first = fftl_stft_first_frame_needed(fb, with_beat) * (int64_t)h->cfg.hop;
+    const int64_t last = (fe - 1) | 1; // the odd frame of the last pair
+    const int64_t e = last * (int64_t)h->cfg.hop + h->cfg.n;
+    *end = e < total ? e : total;
+    return FFTL_OK;
+}
+
+extern "C" int fftl_stft_run_device_span(fftl_stft* h, const int16_t* pcm, int32_t channels, int64_t span_first, int64_t span_samples,
+                                         int64_t total, int64_t cstride, int64_t sstride, int64_t fb, int64_t fe, float* bars,
+                                         int32_t* bars_i32, fftl_beat* beat, void* cuda_stream)
+{
+    int rc = check_run_args(h, pcm, channels, total, fb, fe, bars);
+    if (rc) return rc;
+    if (fe == fb) return FFTL_OK;
+    int64_t need0 = 0, need1 = 0;
+    if ((rc = fftl_stft_sample_span(h, total, fb, fe, beat != nullptr, &need0, &need1))) return rc;
+    if (span_first < 0 || span_samples < 0 || span_first > need0 || span_first + span_samples < need1)
+        return set_error(FFTL_ERR_ARG, "span [%lld,%lld) does not cover the samples frames [%lld,%lld) read: [%lld,%lld) (fftl_stft_sample_span)",
+                         (long long)span_first, (long long)(span_first + span_samples), (long long)fb, (long long)fe, (long long)need0, (long long)need1);
+    int64_t held = span_first + span_samples;
+    if (held > total) held = total;
+    // rebased pointer: element [c*cstride + s*sstride] is absolute sample s; nothing below span_first is ever read
+    // (the run starts at need0 >= span_first) and everything at or beyond `held` reads as zero
+    return run_device_impl(h, pcm - span_first * sstride, channels, held, cstride, sstride, fb, fe, bars, bars_i32, beat, (cudaStream_t)cuda_stream);
 }
 
 // Sum of device times over the run_device calls recorded since the last call
@@ -724,7 +786,15 @@ extern "C" int fftl_stft_run(fftl_stft* h, const int16_t* pcm, int32_t channels,
         if (rc) return rc;
     }
     // chunk size: ~32 MiB of bar output per slot (measured best on c2: 16-32 MiB tie, 8 and 64 lose 5-10 %), at least 512 frames, even
-    static const long long chunk_mib = getenv("FFTL_CHUNK_MIB") ? atoll(getenv("FFTL_CHUNK_MIB")) : 32; // developer knob
+#ifdef FFTL_DEV // developer builds only (python -m fft_lines_b200.build --dev): never in the shipped library
+    static const long long chunk_mib = getenv("FFTL_CHUNK_MIB") ? atoll(getenv("FFTL_CHUNK_MIB")) : 32;
+    static const int dbg_skip = getenv("FFTL_E2E_SKIP") ? atoi(getenv("FFTL_E2E_SKIP")) : 0; // 1 = no H2D, 2 = no D2H
+    static const bool ramp = !getenv("FFTL_CHUNK_NORAMP");
+#else
+    constexpr long long chunk_mib = 32;
+    constexpr int dbg_skip = 0;
+    constexpr bool ramp = true;
+#endif
     int64_t chunk = (int64_t)(chunk_mib << 20) / ((int64_t)channels * B * 4);
     if (chunk < 512) chunk = 512;
     if (chunk > fe - warm) chunk = fe - warm;
@@ -738,12 +808,10 @@ extern "C" int fftl_stft_run(fftl_stft* h, const int16_t* pcm, int32_t channels,
         if (bars_i32 && (rc = ensure_bytes(&h->d_stage[sl][2], &h->stage_bytes[sl][2], sizeof(int32_t) * (size_t)channels * (size_t)chunk * B))) return rc;
         if (beat && (rc = ensure_bytes(&h->d_stage[sl][3], &h->stage_bytes[sl][3], sizeof(fftl_beat) * (size_t)channels * (size_t)chunk))) return rc;
     }
-    static const int dbg_skip = getenv("FFTL_E2E_SKIP") ? atoi(getenv("FFTL_E2E_SKIP")) : 0; // developer knob: 1 = no H2D, 2 = no D2H
     int slot = 0;
     int64_t nchunks = 0;
     // Chunk sizes ramp up at the start and down at the end (chunk/8, /4, /2, chunk ... chunk, half of what is left
     // until chunk/8): the first upload and the last download are the only transfers nothing overlaps with.
-    static const bool ramp = !getenv("FFTL_CHUNK_NORAMP"); // developer A/B switch
     const int64_t min_chunk = ((chunk / 8) + 1) & ~(int64_t)1;
     int64_t step = 0;
     for (int64_t a = warm; a < fe; a += step, slot ^= 1, nchunks++) {
@@ -757,11 +825,10 @@ extern "C" int fftl_stft_run(fftl_stft* h, const int16_t* pcm, int32_t channels,
         int64_t b = a + step < fe ? a + step : fe; // compute frames [a,b)
         int64_t ea = a > fb ? a : fb;                // emit frames [ea,b)
         int64_t ne = b > ea ? b - ea : 0;
-        // chunks are even-sized, so b is even unless it is fe: then frame b (if it exists) is the
-        // partner of b-1 and its samples are uploaded too
-        const int64_t F_all = fftl_stft_num_frames(h, samples);
-        int64_t avail = (b & 1) && b < F_all ? b + 1 : b;
-        int64_t s0 = a * hop, s1 = (avail - 1) * hop + n; // sample span per channel
+        // chunks are even-sized, so b is even unless it is fe: then frame b is the partner of b-1 and its samples
+        // are uploaded too, as far as the job has them (what a device-resident run reads: the signal is zero beyond)
+        int64_t s0 = a * hop, s1 = ((b - 1) | 1) * hop + n; // sample span per channel
+        if (s1 > samples) s1 = samples;
         int64_t span = s1 - s0;
         size_t pcm_bytes = sizeof(int16_t) * (size_t)channels * span;
         size_t bars_bytes = sizeof(float) * (size_t)channels * (size_t)(ne > 0 ? ne : 1) * B;
@@ -794,9 +861,9 @@ extern "C" int fftl_stft_run(fftl_stft* h, const int16_t* pcm, int32_t channels,
             int32_t* d_i32 = bars_i32 ? (int32_t*)h->d_stage[slot][2] : nullptr;
             fftl_beat* d_beat = beat ? (fftl_beat*)h->d_stage[slot][3] : nullptr;
             if (ne > 0)
-                rc = run_range(h, base, channels, dcs, dss, s1, avail, a, ea, b, ea, ne, warm, nf_aux, d_bars, d_i32, beat != nullptr, d_beat, h->stream, nullptr);
+                rc = run_range(h, base, channels, dcs, dss, s1, a, ea, b, ea, ne, warm, nf_aux, d_bars, d_i32, beat != nullptr, d_beat, h->stream, nullptr);
             else // pure beat warm-up chunk: band energy / bass only, nothing emitted
-                rc = run_range(h, base, channels, dcs, dss, s1, avail, a, b, b, b, 1, warm, nf_aux, d_bars, nullptr, beat != nullptr, nullptr, h->stream, nullptr);
+                rc = run_range(h, base, channels, dcs, dss, s1, a, b, b, b, 1, warm, nf_aux, d_bars, nullptr, beat != nullptr, nullptr, h->stream, nullptr);
             if (rc) return rc;
         }
         CUDA_TRY(cudaEventRecord(h->ev_comp[slot], h->stream));
@@ -836,6 +903,8 @@ struct fftl_stream {
     // staging for the host-buffer variant
     int16_t* d_fresh;
     size_t fresh_cap;
+    int16_t* d_conv;        // int16 image of a float capture push (fftl_stream_push_device_f32)
+    size_t conv_cap;
     float* d_bars;
     int32_t* d_bars_i32;
     fftl_beat* d_beat;
@@ -857,6 +926,7 @@ extern "C" void fftl_stream_destroy(fftl_stream* s)
     cudaFree(s->d_tempo_ring);
     cudaFree(s->d_state);
     cudaFree(s->d_fresh);
+    cudaFree(s->d_conv);
     cudaFree(s->d_bars);
     cudaFree(s->d_bars_i32);
     cudaFree(s->d_beat);
@@ -871,12 +941,15 @@ extern "C" int fftl_stream_reset(fftl_stream* s)
     if (!s) return set_error(FFTL_ERR_ARG, "stream handle is NULL");
     CUDA_TRY(cudaSetDevice(s->core->device));
     const size_t S = (size_t)s->streams;
+    CUDA_TRY(cudaDeviceSynchronize()); // pushes still in flight on other streams finish first
     CUDA_TRY(cudaMemset(s->d_window, 0, sizeof(int16_t) * S * s->core->cfg.n));
     CUDA_TRY(cudaMemset(s->d_w_ring, 0, sizeof(int) * S * FFTL_BEAT_SAMPLES));
     CUDA_TRY(cudaMemset(s->d_w_sum, 0, sizeof(int) * S));
     CUDA_TRY(cudaMemset(s->d_tempo_ring, 0, sizeof(int) * S * FFTL_TEMPO_RING));
     CUDA_TRY(cudaMemset(s->d_state, 0, sizeof(StreamState)));
     if (s->d_hist) CUDA_TRY(cudaMemset(s->d_hist, 0, sizeof(float) * S * s->hist_depth * s->core->cfg.bars));
+    // the memsets run on the legacy stream, pushes on non-blocking / caller streams: finish them before returning
+    CUDA_TRY(cudaDeviceSynchronize());
     return FFTL_OK;
 }
 
@@ -894,6 +967,7 @@ extern "C" int fftl_stream_set_history(fftl_stream* s, int32_t depth)
         cudaError_t e = cudaMalloc(&s->d_hist, bytes);
         if (e != cudaSuccess) return set_error(FFTL_ERR_NOMEM, "history allocation failed: %s", cudaGetErrorString(e));
         CUDA_TRY(cudaMemset(s->d_hist, 0, bytes));
+        CUDA_TRY(cudaDeviceSynchronize());
         s->hist_depth = depth;
     }
     return FFTL_OK;
@@ -1001,11 +1075,11 @@ extern "C" int fftl_stream_push_device(fftl_stream* s, const int16_t* fresh, int
         // fast path then packs streams 2k, 2k+1 into its shared sub-transforms (half the transform work of one
         // frame per channel); outputs [1][streams][bars] and aux [1][streams] have the layout of [streams][1][..].
         const long long S = (long long)s->streams * c.n;
-        rc = run_range(h, s->d_window, 1, S, 1, S, s->streams, 0, 0, s->streams, 0, s->streams, 0, s->streams, bars, bars_i32, true, nullptr, st,
+        rc = run_range(h, s->d_window, 1, S, 1, S, 0, 0, s->streams, 0, s->streams, 0, s->streams, bars, bars_i32, true, nullptr, st,
                        nullptr, false, c.n);
     } else {
         // one frame per stream: channels = streams, samples = n
-        rc = run_range(h, s->d_window, s->streams, c.n, 1, c.n, 1, 0, 0, 1, 0, 1, 0, 1, bars, bars_i32, true, nullptr, st, nullptr, true);
+        rc = run_range(h, s->d_window, s->streams, c.n, 1, c.n, 0, 0, 1, 0, 1, 0, 1, bars, bars_i32, true, nullptr, st, nullptr, true);
     }
     if (rc) return rc;
     StreamBeatParams bp;
@@ -1033,6 +1107,32 @@ extern "C" int fftl_stream_push_device(fftl_stream* s, const int16_t* fresh, int
     }
     s->launches += 3;
     return FFTL_OK;
+}
+
+extern "C" int fftl_stream_push_device_f32(fftl_stream* s, const float* fresh, int32_t count, int64_t stride, int64_t sstride, float* bars,
+                                           int32_t* bars_i32, fftl_beat* beat, void* cuda_stream)
+{
+    if (!s) return set_error(FFTL_ERR_ARG, "stream handle is NULL");
+    if (!fresh || !bars) return set_error(FFTL_ERR_ARG, "fresh and bars must not be NULL");
+    if (count < 1 || sstride < 1) return set_error(FFTL_ERR_ARG, "count=%d, sample_stride=%lld: need at least one new sample and a positive stride", count, (long long)sstride);
+    CUDA_TRY(cudaSetDevice(s->core->device));
+    cudaStream_t st = (cudaStream_t)cuda_stream;
+    const size_t need = sizeof(int16_t) * (size_t)s->streams * (((size_t)count + 7) & ~(size_t)7);
+    if (s->conv_cap < need) {
+        // grows on the first push of a given size (not inside a CUDA-graph capture: push once before capturing)
+        CUDA_TRY(cudaStreamSynchronize(st));
+        void* pv = s->d_conv;
+        int rc = ensure_bytes(&pv, &s->conv_cap, need);
+        s->d_conv = (int16_t*)pv;
+        if (rc) return rc;
+    }
+    const int64_t row = ((int64_t)count + 7) & ~(int64_t)7; // rows stay 16-byte aligned for the vector window move
+    long long blocks = ((long long)s->streams * count + 255) / 256;
+    if (blocks > 148 * 8) blocks = 148 * 8;
+    stream_f32_to_i16_kernel<<<(unsigned)blocks, 256, 0, st>>>(fresh, s->d_conv, s->streams, count, stride, sstride, row);
+    CUDA_TRY(cudaGetLastError());
+    s->launches++;
+    return fftl_stream_push_device(s, s->d_conv, count, row, bars, bars_i32, beat, cuda_stream);
 }
 
 extern "C" int fftl_stream_push(fftl_stream* s, const int16_t* fresh, int32_t count, int64_t stride, float* bars, int32_t* bars_i32,
@@ -1304,12 +1404,16 @@ static int compat_beat_state()
     if (compat_stream()) return FFTL_ERR_CUDA;
     CUDA_TRY(cudaMalloc(&g_beat_state, sizeof(CompatBeatState)));
     CUDA_TRY(cudaMemset(g_beat_state, 0, sizeof(CompatBeatState)));
+    CUDA_TRY(cudaDeviceSynchronize()); // g_cstream is non-blocking: it does not order against the legacy stream's memset
     return FFTL_OK;
 }
 
 extern "C" void fftl_compat_reset_beat(void)
 {
-    if (g_beat_state) cudaMemset(g_beat_state, 0, sizeof(CompatBeatState));
+    if (g_beat_state) {
+        cudaMemset(g_beat_state, 0, sizeof(CompatBeatState));
+        cudaDeviceSynchronize();
+    }
     g_beat_value = 0;
     beatMovementPerSec = 0;
     beatposition = 0;
@@ -1338,6 +1442,7 @@ static int plan_init(CompatPlan* p, int n, fftwf_complex* in, fftwf_complex* out
     CUDA_TRY(cudaMalloc(&p->d_out, sizeof(float2) * n));
     CUDA_TRY(cudaMalloc(&p->d_tw, sizeof(float2) * n));
     CUDA_TRY(cudaMemcpy(p->d_tw, tw.data(), sizeof(float2) * n, cudaMemcpyHostToDevice));
+    CUDA_TRY(cudaDeviceSynchronize()); // pageable upload on the legacy stream vs the non-blocking g_cstream
     p->n = n;
     p->in = in;   // the plan is bound to the caller's buffers (fft_calculate.c:24)
     p->out = out;

@@ -24,7 +24,8 @@ struct StftParams {
     long long frame0;      // first frame computed (beat warm-up start)
     long long frame_emit;  // first frame whose bars are written
     long long frame_end;
-    long long frames_total; // frames that exist in the PCM (a pair partner beyond frame_end is still loaded)
+    long long samples;     // samples per channel the caller holds (absolute index); the signal reads as 0 beyond it, so the
+                           // partner of an odd job's last frame is the zero-padded next frame in every kernel and path
     long long nf_emit;     // frame_end - frame_emit   (output stride per channel)
     long long nf_aux;      // aux stride per channel
     long long aux_base;    // aux index of frame0 is (frame0 - aux_base)
@@ -34,6 +35,7 @@ struct StftParams {
     const float2* tw;      // W_n^m
     const int* lo;
     const int* hi;
+    const float* bar_inv;  // 1 / (hi - lo), rounded on the host (the fast path uses the same table)
     const float* sg;       // (2w+1)^2 or nullptr
     float* bars;
     int* bars_i32;
@@ -74,7 +76,7 @@ __global__ void __launch_bounds__(StftShape<N>::THREADS) stft_bars_kernel(const 
     const long long pair = live ? gpair - (long long)ch * p.pairs_per_channel : 0;
     const long long fa = p.frame0 + 2 * pair;
     const bool va = live && fa < p.frame_end, vb = live && fa + 1 < p.frame_end;       // produce outputs for
-    const bool la = live && fa < p.frames_total, lb = live && fa + 1 < p.frames_total; // samples exist for
+    const long long na = live ? p.samples - fa * p.hop : 0, nb = na - p.hop;           // samples that exist of frame a / b
     const int16_t* xa = p.pcm + ch * p.channel_stride + fa * p.hop * p.sample_stride;
     const long long ss = p.sample_stride;
     const long long hs = (long long)p.hop * ss;
@@ -86,8 +88,8 @@ __global__ void __launch_bounds__(StftShape<N>::THREADS) stft_bars_kernel(const 
 #pragma unroll
         for (int r = 0; r < 16; r++) {
             int i = (g + t * G) + r * (N / 16);
-            float a = la ? (float)xa[i * ss] : 0.0f;
-            float b = lb ? (float)xa[i * ss + hs] : 0.0f;
+            float a = i < na ? (float)xa[i * ss] : 0.0f;
+            float b = i < nb ? (float)xa[i * ss + hs] : 0.0f;
             if (p.window) {
                 float w = __ldg(p.window + i);
                 a *= w;
@@ -116,7 +118,7 @@ __global__ void __launch_bounds__(StftShape<N>::THREADS) stft_bars_kernel(const 
             sa += m.x;
             sb += m.y;
         }
-        float inv = 1.0f / (float)(h - l);
+        float inv = __ldg(p.bar_inv + b);
         raw[b] = sa * inv;
         raw[B + b] = sb * inv;
     }
@@ -287,7 +289,7 @@ __device__ __forceinline__ void beat_ring_steps(const double* delta, const doubl
         bool big = false;
 #pragma unroll
         for (int i = 0; i < NF; i++) {
-            mag[i] = sqrtf(f64_to_f32(fma(ar[i], ar[i], ai[i] * ai[i]))); // finite and >= 0
+            mag[i] = __fsqrt_rn(f64_to_f32(fma(ar[i], ar[i], ai[i] * ai[i]))); // finite and >= 0; correctly rounded: exact on perfect squares (--use_fast_math would make sqrtf approximate)
             big |= mag[i] >= 8388608.0f;
         }
         int hv[NF];

@@ -30,7 +30,7 @@ struct RdifParams {
     long long channel_stride;
     long long sample_stride;    // 1 (planar) except in the HOPQ = 0 variant, which also takes interleaved PCM
     long long samples;          // samples per channel (loads beyond it read as 0)
-    long long frame0, frame_emit, frame_end, frames_total;
+    long long frame0, frame_emit, frame_end;
     long long nf_emit, nf_aux, aux_base;
     long long tiles_per_channel;
     long long total_tiles;

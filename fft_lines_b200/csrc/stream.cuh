@@ -82,6 +82,26 @@ __global__ void __launch_bounds__(256) stream_slide_kernel(int16_t* __restrict__
     }
 }
 
+// Capture format -> int16 (wasapi_audio.cpp:398: (int16_t)(source[k] * 65536)).  The float product is truncated to
+// int32 the way the reference's x86 binary does it (cvttss2si: NaN / out of range -> INT32_MIN) and the low 16 bits
+// are kept, which gives the C-undefined cases (|x| >= 0.5) the value the reference's build produces.
+__device__ __forceinline__ int16_t capture_f32_to_i16(float x)
+{
+    return (int16_t)(unsigned short)((unsigned)trunc_i32(__fmul_rn(x, 65536.0f), 1) & 0xffffu);
+}
+
+// out: [streams][out_row] int16 (out_row >= count)
+__global__ void __launch_bounds__(256) stream_f32_to_i16_kernel(const float* __restrict__ fresh, int16_t* __restrict__ out, int streams,
+                                                                int count, long long stream_stride, long long sample_stride, long long out_row)
+{
+    const long long total = (long long)streams * count;
+    for (long long i = (long long)blockIdx.x * blockDim.x + threadIdx.x; i < total; i += (long long)gridDim.x * blockDim.x) {
+        const long long s = i / count;
+        const int k = (int)(i - s * count);
+        out[s * out_row + k] = capture_f32_to_i16(__ldg(fresh + s * stream_stride + k * sample_stride));
+    }
+}
+
 struct StreamBeatParams {
     const int* aux_w;       // [streams] band energy of this tick
     const int* aux_bass;    // [streams] (int)|X[bass_bin]| of this tick
@@ -154,8 +174,8 @@ __global__ void __launch_bounds__(256) stream_beat_kernel(const StreamBeatParams
             float br = v[rr].x - pr_, bi = v[rr].y + pi_;
             const int k = l + 16 * kk;
             if (k <= FFTL_BEAT_SAMPLES) {
-                ha[k] = trunc_i32(0.5f * sqrtf(fmaf(ar, ar, ai * ai)), p.strict);
-                hb[k] = trunc_i32(0.5f * sqrtf(fmaf(br, br, bi * bi)), p.strict);
+                ha[k] = trunc_i32(0.5f * __fsqrt_rn(fmaf(ar, ar, ai * ai)), p.strict); // _rn: these feed (int) casts
+                hb[k] = trunc_i32(0.5f * __fsqrt_rn(fmaf(br, br, bi * bi)), p.strict);
             }
         }
     }

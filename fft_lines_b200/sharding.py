@@ -3,7 +3,8 @@
 Frames are independent up to the bar heights, and the beat stages need only two
 integers per frame of a bounded history (at most 96 + 256 frames back), which
 ``fftl_stft_run*`` recomputes itself for any ``frame_begin``.  So a shard is just a ``[begin, end)`` frame range: no
-data-path collective, only an optional final gather of the outputs.
+data-path collective, only an optional final gather of the outputs.  A rank that holds only its own samples
+(``sample_span``) runs ``fftl_stft_run_device_span`` with the job's absolute frame numbers (``run_shard`` below).
 """
 
 
@@ -31,11 +32,16 @@ def first_frame_needed(frame_begin, with_beat=True):
     return fb & ~1
 
 
-def sample_span(frame_begin, frame_end, n, hop, with_beat=True):
-    """Samples a shard must hold: its frames plus the beat warm-up halo before it."""
+def sample_span(frame_begin, frame_end, n, hop, with_beat=True, total_samples=None):
+    """Samples ``[first, end)`` a shard must hold (mirror of ``fftl_stft_sample_span``): its frames, the beat warm-up
+    halo before them and, when the last frame is even, its pair partner (frames 2k and 2k+1 share packed
+    sub-transforms, so the partner's samples decide the low bits), clipped to the job's ``total_samples``."""
     if frame_end <= frame_begin:
         return 0, 0
-    return first_frame_needed(frame_begin, with_beat) * hop, (frame_end - 1) * hop + n
+    end = ((frame_end - 1) | 1) * hop + n
+    if total_samples is not None:
+        end = min(end, int(total_samples))
+    return first_frame_needed(frame_begin, with_beat) * hop, end
 
 
 def gather_frames(local, total_frames, group=None, dst=None):
@@ -61,3 +67,13 @@ def gather_frames(local, total_frames, group=None, dst=None):
         if rank != dst:
             return None
     return torch.cat([p[:, :e - b] for p, (b, e) in zip(parts, sizes)], dim=1)
+
+
+def run_shard(sp, pcm_span, span_first_sample, total_samples, world_size, rank, want_i32=False, want_beat=True, stream=None):
+    """This rank's frame range of one job through ``fftl_stft_run_device_span``.  ``pcm_span``: torch int16 CUDA
+    [channels, span] holding samples ``sample_span(...)`` of the job.  Returns (frame_begin, frame_end, bars, i32, beat)."""
+    total_frames = sp.num_frames(total_samples)
+    fb, fe = shard_frames(total_frames, world_size, rank)
+    bars, i32, beat = sp.alloc_device_outputs(pcm_span.shape[0], fe - fb, pcm_span.device, want_i32=want_i32, want_beat=want_beat)
+    sp.run_device_span(pcm_span, span_first_sample, total_samples, bars, i32, beat, fb, fe, stream=stream)
+    return fb, fe, bars, i32, beat

@@ -130,6 +130,22 @@ class BatchedSpectrum:
     def launch_count(self):
         return int(_capi.lib().fftl_stft_launch_count(self._h))
 
+    @property
+    def fast_launch_count(self):
+        """How many of the bars-kernel launches took the real-input fast path."""
+        return int(_capi.lib().fftl_stft_fast_launch_count(self._h))
+
+    def set_kernel(self, which):
+        """_capi.KERNEL_AUTO (default) or _capi.KERNEL_GENERIC (the packed-complex baseline kernel)."""
+        _capi.check(_capi.lib().fftl_stft_set_kernel(self._h, which))
+
+    def sample_span(self, total_samples, frame_begin, frame_end, with_beat=True):
+        """Samples [first, end) a frame-range shard of a ``total_samples`` job must hold (fftl_stft_sample_span)."""
+        a, b = C.c_int64(), C.c_int64()
+        _capi.check(_capi.lib().fftl_stft_sample_span(self._h, total_samples, frame_begin, frame_end, 1 if with_beat else 0,
+                                                      C.byref(a), C.byref(b)))
+        return a.value, b.value
+
     def timing(self):
         """(calls, total_ms, bars_kernel_ms) summed over run_device calls since the last timing()."""
         n, t, b = C.c_int32(), C.c_float(), C.c_float()
@@ -197,6 +213,28 @@ class BatchedSpectrum:
             self._h, pcm.data_ptr(), ch, S, pcm.stride(0), pcm.stride(1), frame_begin, frame_end, bars.data_ptr(),
             bars_i32.data_ptr() if bars_i32 is not None else None, beat.data_ptr() if beat is not None else None,
             st.cuda_stream))
+
+    def run_device_span(self, pcm_span, span_first_sample, total_samples, bars, bars_i32=None, beat=None, frame_begin=0,
+                        frame_end=None, stream=None):
+        """Frame-range shard holding only its own samples: ``pcm_span`` (torch int16 CUDA [channels, span]) starts at
+        sample ``span_first_sample`` of a job of ``total_samples`` per channel; frames are numbered as in the whole job."""
+        import torch
+        assert pcm_span.is_cuda and pcm_span.dtype == torch.int16 and pcm_span.dim() == 2
+        ch, span = pcm_span.shape
+        if frame_end is None:
+            frame_end = self.num_frames(total_samples)
+        nf = frame_end - frame_begin
+        B = self.cfg.bars
+        assert bars.is_cuda and bars.dtype == torch.float32 and bars.is_contiguous() and bars.numel() >= ch * nf * B
+        if bars_i32 is not None:
+            assert bars_i32.dtype == torch.int32 and bars_i32.is_contiguous() and bars_i32.numel() >= ch * nf * B
+        if beat is not None:
+            assert beat.is_contiguous() and beat.numel() * beat.element_size() >= ch * nf * BEAT_DTYPE.itemsize
+        st = stream if stream is not None else torch.cuda.current_stream(pcm_span.device)
+        _capi.check(_capi.lib().fftl_stft_run_device_span(
+            self._h, pcm_span.data_ptr(), ch, span_first_sample, span, total_samples, pcm_span.stride(0), pcm_span.stride(1),
+            frame_begin, frame_end, bars.data_ptr(), bars_i32.data_ptr() if bars_i32 is not None else None,
+            beat.data_ptr() if beat is not None else None, st.cuda_stream))
 
     def alloc_device_outputs(self, channels, frames, device, want_i32=False, want_beat=True):
         import torch

@@ -72,6 +72,18 @@ class StreamingSpectrum:
             bars_i32.data_ptr() if bars_i32 is not None else None, beat.data_ptr() if beat is not None else None,
             st.cuda_stream))
 
+    def push_device_f32(self, fresh, bars, bars_i32=None, beat=None, stream=None):
+        """Capture-format push (wasapi_audio.cpp:398): fresh float32 CUDA [streams, count] with any strides, e.g. one
+        channel of interleaved stereo; converted on the device as ``(int16_t)(x * 65536)``."""
+        import torch
+        assert fresh.is_cuda and fresh.dtype == torch.float32 and fresh.dim() == 2 and fresh.shape[0] == self.streams
+        assert bars.is_contiguous() and bars.dtype == torch.float32
+        st = stream if stream is not None else torch.cuda.current_stream(fresh.device)
+        _capi.check(_capi.lib().fftl_stream_push_device_f32(
+            self._h, fresh.data_ptr(), fresh.shape[1], fresh.stride(0), fresh.stride(1), bars.data_ptr(),
+            bars_i32.data_ptr() if bars_i32 is not None else None, beat.data_ptr() if beat is not None else None,
+            st.cuda_stream))
+
     def set_history(self, depth):
         """Keep the last ``depth`` bar frames of every stream on the device (the reference's 3D-mode trail)."""
         _capi.check(_capi.lib().fftl_stream_set_history(self._h, depth))

@@ -109,9 +109,15 @@ void    fftl_stft_destroy(fftl_stft* h);
 int64_t fftl_stft_num_frames(const fftl_stft* h, int64_t samples_per_channel);
 /* First frame a run over [frame_begin, frame_end) reads samples of: frame_begin itself (rounded down to even)
  * without beat output; with beat output the band-energy / bass history it recomputes in front of the range
- * (the start of frame_begin's 96-frame block minus the 256-entry tempo ring, beatDetector.c:53-67).
- * A shard must hold samples [first*hop, (frame_end-1)*hop + n) of every channel. */
+ * (the start of frame_begin's 96-frame block minus the 256-entry tempo ring, beatDetector.c:53-67: up to
+ * 95 + 256 frames back). */
 int64_t fftl_stft_first_frame_needed(int64_t frame_begin, int32_t with_beat);
+/* Samples [*first_sample, *end_sample) of every channel that a run over frames [frame_begin, frame_end) of a job
+ * of total_samples_per_channel samples reads: from frame fftl_stft_first_frame_needed() to the end of the last
+ * frame PAIR (frames 2k and 2k+1 share packed sub-transforms, so an even last frame also reads its partner),
+ * clipped to the job.  This is what a frame-range shard has to hold (fftl_stft_run_device_span). */
+int fftl_stft_sample_span(const fftl_stft* h, int64_t total_samples_per_channel, int64_t frame_begin, int64_t frame_end,
+                          int32_t with_beat, int64_t* first_sample, int64_t* end_sample);
 
 /* PCM addressing: sample s of channel c is pcm[c*channel_stride + s*sample_stride]
  * (planar: channel_stride = samples, sample_stride = 1; interleaved: 1, channels).
@@ -119,9 +125,13 @@ int64_t fftl_stft_first_frame_needed(int64_t frame_begin, int32_t with_beat);
  *   bars     [channels][frame_end-frame_begin][bars] float   (height before the (int) cast)
  *   bars_i32 same shape, int32, the reference's BARINFO.height      (may be NULL)
  *   beat     [channels][frame_end-frame_begin]                       (may be NULL)
- * Beat outputs are those of a reference run started at frame 0: the up-to-255
- * frames before frame_begin are recomputed internally (frame-range shards need
- * no neighbour exchange).
+ * Beat outputs are those of a reference run started at frame 0: the band energy /
+ * bass of up to 351 frames before frame_begin is recomputed internally
+ * (fftl_stft_first_frame_needed; frame-range shards need no neighbour exchange).
+ * The signal reads as zero beyond samples_per_channel (only the pair partner of
+ * an odd job's last frame ever looks there).
+ * ONE call per handle may be in flight at a time: the handle owns the scratch
+ * between its two kernels.  Use one handle per stream / thread / GPU.
  * Restates for all frames: fft_lines.c:190-231 (bars), :281 + beatDetector.c:30-44
  * (band energy), :233-236 + beatDetector.c:51-106 (tempo).                       */
 int fftl_stft_run_device(fftl_stft* h, const int16_t* pcm_dev, int32_t channels,
@@ -129,6 +139,16 @@ int fftl_stft_run_device(fftl_stft* h, const int16_t* pcm_dev, int32_t channels,
                          int64_t sample_stride, int64_t frame_begin, int64_t frame_end,
                          float* bars_dev, int32_t* bars_i32_dev, fftl_beat* beat_dev,
                          void* cuda_stream /* cudaStream_t; NULL = CUDA's default stream */);
+
+/* Frame-range shard that holds ONLY its own samples (multi-GPU sharding): pcm_dev points at sample
+ * span_first_sample of every channel and holds span_samples of them; frame numbers, outputs and beat records
+ * are those of the whole job of total_samples_per_channel samples (no re-basing on the caller's side, so the
+ * tempo ring slot and the beat blocks of a frame are those of a single-GPU run: results are bit-identical).
+ * The span must cover fftl_stft_sample_span(); FFTL_ERR_ARG otherwise. */
+int fftl_stft_run_device_span(fftl_stft* h, const int16_t* pcm_dev, int32_t channels, int64_t span_first_sample,
+                              int64_t span_samples, int64_t total_samples_per_channel, int64_t channel_stride,
+                              int64_t sample_stride, int64_t frame_begin, int64_t frame_end, float* bars_dev,
+                              int32_t* bars_i32_dev, fftl_beat* beat_dev, void* cuda_stream);
 
 /* Same, host buffers.  Copies are chunked by frame range and overlapped with
  * the kernels on three streams; buffers from fftl_host_alloc (pinned) make the
@@ -138,8 +158,14 @@ int fftl_stft_run(fftl_stft* h, const int16_t* pcm_host, int32_t channels,
                   int64_t sample_stride, int64_t frame_begin, int64_t frame_end,
                   float* bars_host, int32_t* bars_i32_host, fftl_beat* beat_host);
 
-/* Number of kernel launches issued by this handle since creation. */
+/* Number of kernel launches issued by this handle since creation; how many of them were the fast path. */
 int64_t fftl_stft_launch_count(const fftl_stft* h);
+int64_t fftl_stft_fast_launch_count(const fftl_stft* h);
+/* Which bars kernel a handle uses: AUTO = the real-input fast path wherever it is built (n = 1024..16384), else the
+ * generic packed-complex kernel; GENERIC = always the latter (the correctness baseline the fast path is tested
+ * against).  Both are this library's own sm_100a kernels. */
+enum { FFTL_KERNEL_AUTO = 0, FFTL_KERNEL_GENERIC = 1 };
+int fftl_stft_set_kernel(fftl_stft* h, int32_t which);
 /* Device time (ms, CUDA events recorded on the launching stream) summed over
  * the fftl_stft_run_device calls made since the previous fftl_stft_timing call
  * (at most the last 64): whole call, and the dominant stft_bars kernel only.
@@ -167,6 +193,14 @@ int  fftl_stream_push_device(fftl_stream* s, const int16_t* fresh_dev, int32_t c
                              float* bars_dev, int32_t* bars_i32_dev, fftl_beat* beat_dev, void* cuda_stream);
 int  fftl_stream_push(fftl_stream* s, const int16_t* fresh_host, int32_t count, int64_t stream_stride,
                       float* bars_host, int32_t* bars_i32_host, fftl_beat* beat_host);
+/* Capture-format input (wasapi_audio.cpp:390-400, :458-466): the reference receives 32-bit float samples and
+ * stores (int16_t)(x * 65536), which is undefined in C for |x*65536| >= 32768 (|x| >= 0.5).  Here the
+ * conversion is DEFINED as what the reference's x86 binary does: truncate toward zero to int32
+ * (cvttss2si: NaN and out-of-range give INT32_MIN), keep the low 16 bits.  fresh: [streams][count] float,
+ * element (s, k) at fresh[s*stream_stride + k*sample_stride] (WASAPI stereo interleaved: sample_stride = 2). */
+int  fftl_stream_push_device_f32(fftl_stream* s, const float* fresh_dev, int32_t count, int64_t stream_stride,
+                                 int64_t sample_stride, float* bars_dev, int32_t* bars_i32_dev, fftl_beat* beat_dev,
+                                 void* cuda_stream);
 int64_t fftl_stream_launch_count(const fftl_stream* s);
 /* Render-side history (the reference's "3D mode" keeps the last ~96 bar frames on screen by feeding the
  * bitmap back, drawBar2D.cpp:405-426,670-680).  depth > 0 keeps the last `depth` float bar frames of every

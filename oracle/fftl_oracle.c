@@ -318,6 +318,35 @@ void orc_tempo_hb(const int32_t* ring, int strict, int32_t* hb)
         hb[i] = orc_trunc_i32(sqrt(orr[i] * orr[i] + oi[i] * oi[i]), strict);
 }
 
+/* The magnitudes of beatDetector.c:73 BEFORE the (int) cast, bins 0..160, in double: what the parity tests use
+ * to tell an integer-boundary flip of the peak scan from a wrong transform. */
+void orc_tempo_mag(const int32_t* ring, double* mag)
+{
+    double ir[FFTL_TEMPO_RING], orr[FFTL_TEMPO_RING], oi[FFTL_TEMPO_RING];
+    for (int i = 0; i < FFTL_TEMPO_RING; i++) ir[i] = (double)(float)ring[i];
+    orc_fft(FFTL_TEMPO_RING, ir, NULL, orr, oi);
+    for (int i = 0; i <= FFTL_BEAT_SAMPLES; i++) mag[i] = sqrt(orr[i] * orr[i] + oi[i] * oi[i]);
+}
+
+/* Tempo-ring magnitudes (orc_tempo_mag, 161 doubles) after each of `count` frames whose bass values are given,
+ * the ring starting zeroed at slot first_frame % 256; ring_norm[f] = Euclidean norm of the ring (may be NULL). */
+void orc_tempo_mag_replay(const int32_t* bass, int64_t count, int64_t first_frame, double* mag_out, double* ring_norm)
+{
+    int32_t ring[FFTL_TEMPO_RING];
+    memset(ring, 0, sizeof(ring));
+    int pos = (int)(first_frame % FFTL_TEMPO_RING);
+    for (int64_t f = 0; f < count; f++) {
+        ring[pos] = bass[f];
+        pos = (pos + 1) % FFTL_TEMPO_RING;
+        orc_tempo_mag(ring, mag_out + f * (FFTL_BEAT_SAMPLES + 1));
+        if (ring_norm) {
+            double s2 = 0;
+            for (int i = 0; i < FFTL_TEMPO_RING; i++) s2 += (double)ring[i] * (double)ring[i];
+            ring_norm[f] = sqrt(s2);
+        }
+    }
+}
+
 int32_t orc_peak_pick(const int32_t* hb)
 {
     /* beatDetector.c:78-103 */

@@ -65,6 +65,8 @@ void orc_bass_beat(orc_beat_state* s, int32_t bass, int n, float time_delta, int
 int32_t orc_peak_pick(const int32_t* hb);
 /* hb[161] of a 256-entry ring (beatDetector.c:61-75). */
 void orc_tempo_hb(const int32_t* ring, int strict, int32_t* hb);
+void orc_tempo_mag(const int32_t* ring, double* mag);
+void orc_tempo_mag_replay(const int32_t* bass, int64_t count, int64_t first_frame, double* mag_out, double* ring_norm);
 
 /* Whole chain over frames [frame_begin, frame_end) of every channel, as
  * fftl_stft_run defines it.  Any output pointer may be NULL. */

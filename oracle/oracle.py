@@ -125,6 +125,7 @@ def lib():
         L.orc_peak_pick.restype = C.c_int32
         L.orc_peak_pick.argtypes = [i32p]
         L.orc_tempo_hb.argtypes = [i32p, C.c_int, i32p]
+        L.orc_tempo_mag_replay.argtypes = [i32p, C.c_int64, C.c_int64, f64p, f64p]
         L.orc_stft.argtypes = [C.POINTER(Config), i16p, C.c_int32, C.c_int64, C.c_int64, C.c_int64,
                                C.c_int64, C.c_int64, f64p, f32p, i32p, C.c_void_p]
         L.orc_beat_replay.argtypes = [C.POINTER(Config), i32p, i32p, C.c_int64, C.c_int64, C.c_void_p, i32p]
@@ -275,6 +276,17 @@ def tempo_hb(ring, strict=1):
     hb = np.empty(BEAT_SAMPLES + 1, np.int32)
     lib().orc_tempo_hb(_p(ring, C.c_int32), strict, _p(hb, C.c_int32))
     return hb
+
+
+def tempo_mag_replay(bass, first_frame=0):
+    """fp64 magnitudes |X256[0..160]| of the tempo ring after every frame (before the reference's (int) cast,
+    beatDetector.c:73) and the ring's Euclidean norm: (mag [frames,161], norm [frames])."""
+    bass = np.ascontiguousarray(bass, np.int32)
+    n = bass.shape[0]
+    mag = np.empty((n, BEAT_SAMPLES + 1), np.float64)
+    norm = np.empty(n, np.float64)
+    lib().orc_tempo_mag_replay(_p(bass, C.c_int32), n, first_frame, _p(mag, C.c_double), _p(norm, C.c_double))
+    return mag, norm
 
 
 def synth_pcm(channels, samples, first_sample=0, sample_rate=48000.0, seed=0x5EED0000):

@@ -16,6 +16,12 @@
  *   WM_DESTROY fft_lines.c:420-433   cleanup order
  * Everything the reference computes with its own functions (plans, execute,
  * AddBeatSample, GetBeatValue, BassBeatDetector) runs the reference's code.
+ *
+ * Same harness, other provider: compiled with -DFFTL_HARNESS_CUDA_PROVIDER and
+ * -I<repo>/include, and linked with -lfftlines_cuda INSTEAD of the two
+ * reference files and the FFT shim, the very same restated WndProc drives the
+ * drop-in library (tests/test_gpu_dropin_c.py replays the golden fixtures
+ * through it).  Only what reaches into the reference's private state differs.
  */
 #include <stdint.h>
 #include <stdlib.h>
@@ -23,6 +29,17 @@
 #include <math.h>
 #include <time.h>
 
+#ifdef FFTL_HARNESS_CUDA_PROVIDER
+#include "fft_calculate.h"         /* this repo's include/: the reference's prototypes, fft_calculate.h:5-11 */
+#include "beatDetector.h"          /* ... beatDetector.h:3-11                                                 */
+#include "fftlines.h"              /* fftl_set_n, fftl_compat_reset_beat, fftl_last_error                      */
+#define N 2048                     /* global.h:3                       */
+#define DEFAULT_BEATBBUFFERSIZE 256 /* settingsFile.h:11                */
+int* bassBeatBuffer = NULL;        /* settingsFile.c:83: the application owns it; the library mirrors its ring here */
+static int beatFramesRecorded = 0; /* the harness's own copy of beatDetector.c:23 (slot written by the next call) */
+static int BeatThreshold = 0;      /* not exported by the drop-in: reported as 0 */
+static void fftwf_cleanup(void) {}
+#else
 #include <fftw3.h>                 /* the reference's vendored header */
 #include "global.h"                /* reference: N, globalhwnd         */
 #include "settingsFile.h"          /* reference: constants, externs    */
@@ -38,6 +55,7 @@ extern int beatValues[160];
 extern int currentBeatValue, sumOfBeatValues, BeatThreshold, beatValue, beatFramesRecorded;
 
 extern int fftl_shim_override_n;   /* oracle/fftwf_shim.c */
+#endif
 
 static fftwf_complex *input, *output, *beatinput, *beatoutput; /* fft_lines.c:63-67 */
 static int g_n = N;
@@ -48,11 +66,17 @@ int ref_open(int n)
 {
     /* fft_lines.c:110-116.  n != N only through the shim's size override. */
     g_n = n > 0 ? n : N;
+#ifdef FFTL_HARNESS_CUDA_PROVIDER
+    fftl_set_n(g_n);
+#else
     fftl_shim_override_n = (g_n != N) ? g_n : 0;
+#endif
     input = (fftwf_complex*)malloc(sizeof(fftwf_complex) * g_n);
     output = (fftwf_complex*)malloc(sizeof(fftwf_complex) * g_n);
     initializefft(input, output);
+#ifndef FFTL_HARNESS_CUDA_PROVIDER
     fftl_shim_override_n = 0;
+#endif
     beatinput = (fftwf_complex*)malloc(sizeof(fftwf_complex) * DEFAULT_BEATBBUFFERSIZE);
     beatoutput = (fftwf_complex*)malloc(sizeof(fftwf_complex) * DEFAULT_BEATBBUFFERSIZE);
     initializefft256(beatinput, beatoutput);
@@ -63,8 +87,13 @@ int ref_open(int n)
 
 void ref_reset_beat(void)
 {
+#ifdef FFTL_HARNESS_CUDA_PROVIDER
+    fftl_compat_reset_beat();
+    beatFramesRecorded = 0;
+#else
     memset(beatValues, 0, sizeof(beatValues));
     currentBeatValue = sumOfBeatValues = BeatThreshold = beatValue = beatFramesRecorded = 0;
+#endif
     beatMovementPerSec = 0; beatposition = 0; timeDelta = 0; direction = 0;
     if (bassBeatBuffer) memset(bassBeatBuffer, 0, sizeof(int) * DEFAULT_BEATBBUFFERSIZE);
 }
@@ -96,6 +125,9 @@ void ref_execute256(const float* in_interleaved, float* out_interleaved)
 void ref_add_beat_sample(int w) { AddBeatSample(w); }
 int  ref_get_beat_value(void) { return GetBeatValue(); }
 int  ref_get_threshold(void) { return BeatThreshold; }
+#ifdef FFTL_HARNESS_CUDA_PROVIDER
+int  ref_provider_error(void) { return fftl_last_error(); }
+#endif
 float ref_get_movement(void) { return beatMovementPerSec; }
 
 typedef struct ref_frame_out {
@@ -150,6 +182,9 @@ void ref_tick(const int16_t* left, const int16_t* right, int barCount, float zoo
         fo->bass = beatDetection ? bassBeatBuffer[slot] : 0;
         fo->movement_per_sec = beatMovementPerSec;
     }
+#ifdef FFTL_HARNESS_CUDA_PROVIDER
+    if (beatDetection) beatFramesRecorded = (beatFramesRecorded + 1) % DEFAULT_BEATBBUFFERSIZE; /* beatDetector.c:54-59 */
+#endif
 }
 
 /* Batched run of the reference tick over strided frames of planar PCM

@@ -7,6 +7,8 @@ import ctypes as C
 import numpy as np
 import pytest
 
+from helpers import assert_peaks_explained
+
 pytestmark = pytest.mark.gpu
 
 
@@ -54,10 +56,9 @@ def test_c2_full_hour_properties(oracle, lib):
             assert (np.abs(got - ref) <= 1e-4 * np.abs(ref).max(axis=-1, keepdims=True)).all(), f
         # (5) beat chain over the whole hour replayed bit-exactly from the GPU's own integers
         b = lib.BatchedSpectrum.beat_to_numpy(beat)
-        rep = oracle.beat_replay(ocfg, b["w"][0, :40000], b["bass"][0, :40000])
-        for k in ("thr", "beat_value", "flag"):
-            assert (rep[k] == b[k][0, :40000]).all(), k
-        assert (rep["peak_index"] == b["peak_index"][0, :40000]).mean() > 0.97
+        #     (a differing tempo peak index must be explained as an integer-boundary flip: helpers.assert_peaks_explained)
+        for ch in range(2):
+            assert_peaks_explained(oracle, ocfg, b[ch, :40000], "c2 channel %d" % ch)
         assert b["flag"].sum() > 0
 
 

@@ -31,6 +31,10 @@ def test_sample_span_includes_beat_halo(lib):
     assert sh.sample_span(1001, 2000, 4096, 512, with_beat=False) == (1000 * 512, 1999 * 512 + 4096)
     assert sh.sample_span(100, 200, 4096, 512) == (0, 199 * 512 + 4096)
     assert sh.sample_span(5, 5, 4096, 512) == (0, 0)
+    # an even last frame shares its packed sub-transforms with its partner: the partner's samples belong to the span,
+    # as far as the job has them
+    assert sh.sample_span(1000, 2001, 4096, 512) == ((960 - 256) * 512, 2001 * 512 + 4096)
+    assert sh.sample_span(1000, 2001, 4096, 512, total_samples=2000 * 512 + 4096 + 100) == ((960 - 256) * 512, 2000 * 512 + 4096 + 100)
 
 
 def _worker(rank, world, port, tmp):
@@ -46,7 +50,7 @@ def _worker(rank, world, port, tmp):
     S = 1024 + 256 * 600
     total = O.num_frames(cfg, S)
     b, e = sh.shard_frames(total, world, rank)
-    s0, s1 = sh.sample_span(b, e, cfg.n, cfg.hop)
+    s0, s1 = sh.sample_span(b, e, cfg.n, cfg.hop, True, S)
     # each rank only materialises its own sample span (plus halo), like a GPU shard would
     local_pcm = O.synth_pcm(2, s1 - s0, first_sample=s0)
     f_off = s0 // cfg.hop

@@ -12,7 +12,14 @@ collective, so N GPUs run N such batches ("weak" scaling).
             PCM in, host bars + beat records out, copies inside the timed region
   roofline  the dominant kernel (stft_bars) against its FP32 compute roofline
             (5*N*log2 N flop per frame) and its HBM byte roofline
-  cpu_baseline  the CPU port of the reference chain on this box's host cores
+  sharded   BASELINE configs[4] in small: ONE 8-channel job cut into frame ranges (sharding.shard_frames), every
+            rank generating and holding only its own sample span and running fftl_stft_run_device_span; strong-
+            scaling efficiency against the same job on one GPU, every shard compared bit for bit with the
+            single-GPU result, and the NCCL gather of the outputs timed separately
+  sustained the same step back to back for >= 3 s with the clock sampler running
+  latency   BASELINE configs[2]: one tick of 1024 streams x 1024 points through the streaming front end
+  cpu_baseline  the CPU port of the reference chain on this box's host cores (all cores and one thread) and the
+            same chain on library FFTs (pocketfft, torch.fft)
 
 `--impl reference` times the reference's CPU implementation of the same
 configuration instead (oracle/ port: the reference has no Hann/log/SG stages
@@ -48,8 +55,9 @@ def measured_peaks():
 class ClockSampler:
     """Samples SM clock / throttle reasons of one GPU while the timed region runs."""
 
-    def __init__(self, index):
+    def __init__(self, index, power=False):
         self.index = index
+        self.power = [] if power else None
         self.samples = []
         self.reasons = set()
         self.max_mhz = None
@@ -78,6 +86,8 @@ class ClockSampler:
         while not self._stop.is_set():
             try:
                 self.samples.append(nv.nvmlDeviceGetClockInfo(self._h, nv.NVML_CLOCK_SM))
+                if self.power is not None:
+                    self.power.append(nv.nvmlDeviceGetPowerUsage(self._h) / 1000.0)
                 if getr:
                     bits = getr(self._h)
                     for v, k in names.items():
@@ -100,7 +110,11 @@ class ClockSampler:
         if self.samples:
             s = sorted(self.samples)
             out["sm_mhz"] = s[len(s) // 2]
+            out["sm_min_mhz"] = s[0]
             out["samples"] = len(s)
+        if self.power:
+            pw = sorted(self.power)
+            out["power_w_median"], out["power_w_max"] = pw[len(pw) // 2], pw[-1]
         return out
 
 
@@ -129,6 +143,244 @@ def cpu_leg(threads, target_seconds=12.0):
     want = min(SECONDS, max(30, int(target_seconds * rate / CHANNELS * HOP / FS)))
     pcm = O.synth_pcm(CHANNELS, FS * want)
     return O, cfg, pcm, threads, want
+
+
+def cpu_baselines():
+    """Three CPU figures for the same chain on this box (bounded samples, ~25 s in all): the fp32 port of the
+    reference chain on all cores (the reference-shaped arm: scalar code, this repo's FFT shim), the same port on ONE
+    thread (how the reference actually runs, fft_lines.c:161-288), and the chain on library FFTs on all cores."""
+    O, cfg, pcm, threads, want = cpu_leg(None, target_seconds=8.0)
+    frames = CHANNELS * O.num_frames(cfg, pcm.shape[1])
+    sec, _ = O.port_run(cfg, pcm, threads=threads, want_i32=False)
+    out = {"value": frames / sec, "unit": "frames/s", "cores": threads, "kind": "port",
+           "fft_provider": "fftwf-shim (this repo's scalar radix-4 FFT: no host FFTW in this image)",
+           "sample": "first %d s of the same workload (%d frames), fp32 port of the reference chain" % (want, frames),
+           "seconds": sec, "others": []}
+    n1 = max(10, want // threads)
+    p1 = pcm[:, :FS * n1]
+    f1 = CHANNELS * O.num_frames(cfg, p1.shape[1])
+    sec1, _ = O.port_run(cfg, p1, threads=1, want_i32=False)
+    out["others"].append({"value": f1 / sec1, "unit": "frames/s", "cores": 1, "kind": "port", "fft_provider": "fftwf-shim",
+                          "sample": "first %d s (%d frames), one thread as the reference runs" % (n1, f1), "seconds": sec1})
+    try:
+        from oracle import numpy_chain as NC
+        for prov, label in (("scipy", "pocketfft (scipy.fft.rfft)"), ("torch", "torch.fft.rfft (CPU)")):
+            NC.run(O, cfg, pcm[:, :FS * 5], provider=prov)  # warm-up: imports, plans, thread pool
+            t0 = time.perf_counter()
+            r = NC.run(O, cfg, pcm, provider=prov)
+            dt = time.perf_counter() - t0
+            out["others"].append({"value": frames / dt, "unit": "frames/s", "cores": r["workers"], "kind": "port",
+                                  "fft_provider": label, "seconds": dt,
+                                  "sample": "first %d s (%d frames): batched real FFT + the same Hann / log-bin / SG / beat "
+                                            "tail in numpy, blocks of frames over all cores (oracle/numpy_chain.py)" % (want, frames)})
+    except Exception as e:  # a missing library must not cost the bench line
+        out["others"].append({"fft_provider": "library FFT line unavailable", "error": str(e)})
+    best = max([out] + [o for o in out["others"] if "value" in o], key=lambda o: o["value"])
+    out["best"] = {"value": best["value"], "fft_provider": best["fft_provider"], "cores": best["cores"]}
+    return out
+
+
+
+SHARD_CHANNELS, SHARD_SECONDS = 8, 7200   # configs[4] in small: 8 channels x 2 h (1000 h is the same loop run longer)
+
+
+def _bit_hash(t):
+    """Order-sensitive 64-bit checksum of a tensor's raw 32-bit words (wraps mod 2^64), computed on its device."""
+    import torch
+    w = t.contiguous().view(torch.int32).reshape(-1).to(torch.int64)
+    idx = torch.arange(w.numel(), device=w.device, dtype=torch.int64)
+    return int(((w & 0xffffffff) * (idx % 1000003 + 1)).sum().item())
+
+
+def sharded_leg(F, sp, dev, rank, world, barrier, max_over_ranks, steps):
+    """One fixed 8-channel job, frame-range sharded over the ranks: no data-path collective.
+    Every rank generates ONLY its own sample span on its device and runs it with the job's absolute frame numbers.
+    Rank 0 also runs the whole job alone: the 1-GPU time of the same job and the single-GPU result every shard is
+    compared with bit for bit (order-sensitive checksums of whole shards + the frames either side of every cut)."""
+    import torch
+    import torch.distributed as dist
+    from fft_lines_b200 import sharding as sh
+    S = FS * SHARD_SECONDS
+    total_frames = sp.num_frames(S)
+    stream = torch.cuda.current_stream(dev)
+    EDGE = 8
+
+    def timed(fn, k):
+        for _ in range(2):
+            fn()
+        torch.cuda.synchronize()
+        e0, e1 = torch.cuda.Event(enable_timing=True), torch.cuda.Event(enable_timing=True)
+        e0.record(stream)
+        for _ in range(k):
+            fn()
+        e1.record(stream)
+        torch.cuda.synchronize()
+        return e0.elapsed_time(e1) / k
+
+    # ---- the same job on one GPU (rank 0 alone; the other ranks wait at the barrier)
+    t1 = 0.0
+    full_hash, full_edges = None, None
+    if rank == 0:
+        pcm = torch.empty((SHARD_CHANNELS, S), dtype=torch.int16, device=dev)
+        F.synth_pcm_device(pcm)
+        fbars, _, fbeat = sp.alloc_device_outputs(SHARD_CHANNELS, total_frames, dev)
+        t1 = timed(lambda: sp.run_device(pcm, fbars, None, fbeat), steps)
+        del pcm
+        full_hash, full_edges = [], []
+        for r in range(world):
+            b, e = sh.shard_frames(total_frames, world, r)
+            full_hash.append((_bit_hash(fbars[:, b:e]), _bit_hash(fbeat[:, b:e])))
+            full_edges.append((fbars[:, b:b + EDGE].clone(), fbars[:, e - EDGE:e].clone(), fbeat[:, b:b + EDGE].clone(), fbeat[:, e - EDGE:e].clone()))
+        del fbars, fbeat
+        torch.cuda.empty_cache()
+    barrier()
+    t1 = max_over_ranks(t1)
+
+    # ---- this rank's shard: its sample span only
+    fb, fe = sh.shard_frames(total_frames, world, rank)
+    s0, s1 = sp.sample_span(S, fb, fe, True)
+    assert (s0, s1) == sh.sample_span(fb, fe, N_FFT, HOP, True, S)
+    span = torch.empty((SHARD_CHANNELS, s1 - s0), dtype=torch.int16, device=dev)
+    F.synth_pcm_device(span, first_sample=s0)
+    bars, _, beat = sp.alloc_device_outputs(SHARD_CHANNELS, fe - fb, dev)
+    barrier()
+    tn = max_over_ranks(timed(lambda: sp.run_device_span(span, s0, S, bars, None, beat, fb, fe), steps))
+    mine = torch.tensor([_bit_hash(bars), _bit_hash(beat)], dtype=torch.int64, device=dev)
+    edges = [bars[:, :EDGE].contiguous(), bars[:, -EDGE:].contiguous(), beat[:, :EDGE].contiguous(), beat[:, -EDGE:].contiguous()]
+    ok_hash = ok_edges = True
+    if world > 1:
+        hashes = [torch.empty_like(mine) for _ in range(world)]
+        dist.all_gather(hashes, mine)
+        gathered = []
+        for t in edges:
+            parts = [torch.empty_like(t) for _ in range(world)] if rank == 0 else None
+            dist.gather(t, parts, dst=0)
+            gathered.append(parts)
+    else:
+        hashes, gathered = [mine], [[t] for t in edges]
+    if rank == 0:
+        for r in range(world):
+            ok_hash &= (int(hashes[r][0]), int(hashes[r][1])) == full_hash[r]
+            ok_edges &= all(torch.equal(gathered[q][r], full_edges[r][q]) for q in range(4))
+    # ---- optional final gather of the outputs over NCCL (not part of the path; timed on its own)
+    gather = None
+    if world > 1:
+        def g():
+            return sh.gather_frames(bars, total_frames)
+        g()
+        torch.cuda.synchronize()
+        barrier()
+        e0, e1 = torch.cuda.Event(enable_timing=True), torch.cuda.Event(enable_timing=True)
+        e0.record(stream)
+        allb = g()
+        e1.record(stream)
+        torch.cuda.synchronize()
+        gms = max_over_ranks(e0.elapsed_time(e1))
+        nbytes = allb.numel() * 4
+        gather = {"what": "all-gather of the float bars onto every rank (NCCL, sharding.gather_frames)", "ms": gms,
+                  "bytes": int(nbytes), "gb_per_s_per_rank": nbytes / (gms * 1e-3) / 1e9}
+        del allb
+    frames = SHARD_CHANNELS * total_frames
+    halo = SHARD_CHANNELS * (fb - s0 // HOP) if fe > fb else 0
+    rec = {"job": "%d channels x %d s, 4096-pt Hann, hop 512, 200 bars + beat: %d frames, frame-range sharded over %d GPU(s)"
+                  % (SHARD_CHANNELS, SHARD_SECONDS, frames, world),
+           "api": "fftl_stft_run_device_span (each rank holds only sharding.sample_span of the PCM, generated on its own device)",
+           "frames": frames, "ms_one_gpu": t1, "ms_sharded": tn, "frames_per_s": frames / (tn * 1e-3),
+           "speedup": t1 / tn, "efficiency": t1 / (world * tn), "scaling": "strong",
+           "halo_frames_recomputed_per_rank": int(halo), "collective_in_path": None,
+           "bit_exact_vs_one_gpu": bool(ok_hash), "rank_boundaries_bit_exact": bool(ok_edges),
+           "boundary_check": "first and last %d frames of every shard (bars and beat records) torch.equal to the single-GPU run; "
+                             "order-sensitive 64-bit checksums of every whole shard equal" % EDGE,
+           "gather": gather}
+    del span, bars, beat
+    torch.cuda.empty_cache()
+    return rec
+
+
+def sustained_leg(sp, pcm, bars, beat, dev, local_rank, frames_per_step, world, barrier, max_over_ranks, seconds=3.0):
+    """The step back to back for >= `seconds` with the clock sampler running: what the kernel holds, not a burst."""
+    import torch
+    stream = torch.cuda.current_stream(dev)
+    sampler = ClockSampler(physical_gpu_index(local_rank), power=True)
+    barrier()
+    sampler.start()
+    e0, e1 = torch.cuda.Event(enable_timing=True), torch.cuda.Event(enable_timing=True)
+    t0 = time.perf_counter()
+    e0.record(stream)
+    n = 0
+    while True:
+        for _ in range(50):
+            sp.run_device(pcm, bars, None, beat)
+        n += 50
+        torch.cuda.synchronize()
+        if time.perf_counter() - t0 >= seconds:
+            break
+    e1.record(stream)
+    torch.cuda.synchronize()
+    clocks = sampler.stop()
+    ms = e0.elapsed_time(e1)
+    per_step = max_over_ranks(ms / n)
+    return {"seconds": ms * 1e-3, "steps": n, "ms_per_step": per_step, "value": world * frames_per_step / (per_step * 1e-3),
+            "unit": "frames/s", "clocks": clocks}
+
+
+def latency_leg(F, dev):
+    """BASELINE configs[2]: 1024 concurrent mono streams, 1024-point window, 64 bars; one tick (512 new samples per
+    stream) per batch through the streaming front end (windows and beat state resident on the device)."""
+    import numpy as np
+    import torch
+    STREAMS, COUNT, B = 1024, 512, 64
+    cfg3 = F.extended_config(1024, COUNT, B)
+    src = torch.empty((STREAMS, COUNT * 8), dtype=torch.int16, device=dev)
+    F.synth_pcm_device(src)
+    pct = lambda a: {"p50_us": float(np.percentile(a, 50)), "p99_us": float(np.percentile(a, 99))}
+    with F.StreamingSpectrum(cfg3, STREAMS, device=dev.index) as ss:
+        fresh = src[:, :COUNT].contiguous()
+        bars = torch.empty((STREAMS, B), dtype=torch.float32, device=dev)
+        beat = torch.empty((STREAMS, 8), dtype=torch.int32, device=dev)
+        st = torch.cuda.Stream(dev)
+        with torch.cuda.stream(st):
+            l0 = ss.launch_count
+            for _ in range(5):
+                ss.push_device(fresh, bars, None, beat, stream=st)
+            st.synchronize()
+            per_tick = (ss.launch_count - l0) // 5
+            g = torch.cuda.CUDAGraph()
+            with torch.cuda.graph(g, stream=st):
+                ss.push_device(fresh, bars, None, beat, stream=st)
+            lat = []
+            for _ in range(1500):
+                t0 = time.perf_counter()
+                g.replay()
+                st.synchronize()
+                lat.append((time.perf_counter() - t0) * 1e6)
+            lat_graph = np.array(lat[300:])
+            e0, e1 = torch.cuda.Event(enable_timing=True), torch.cuda.Event(enable_timing=True)
+            e0.record(st)
+            for _ in range(500):
+                g.replay()
+            e1.record(st)
+            st.synchronize()
+            dev_us = e0.elapsed_time(e1) * 1e3 / 500
+        h_fresh = F.PinnedArray((STREAMS, COUNT), np.int16)
+        h_fresh.array[:] = fresh.cpu().numpy()
+        hb, hbt = F.PinnedArray((STREAMS, B), np.float32), F.PinnedArray((STREAMS,), F.BEAT_DTYPE)
+        o = {"bars": hb.array, "beat": hbt.array}
+        for _ in range(20):
+            ss.push(h_fresh.array, want_i32=False, out=o)
+        lat = []
+        for _ in range(800):
+            t0 = time.perf_counter()
+            ss.push(h_fresh.array, want_i32=False, out=o)
+            lat.append((time.perf_counter() - t0) * 1e6)
+        lat_host = np.array(lat[100:])
+        h_fresh.free(); hb.free(); hbt.free()
+    return {"workload": "c3: 1024 concurrent mono streams, 1024-pt Hann, 64 log bars + SG + beat, one tick (512 new samples per stream) per batch",
+            "frames_per_batch": STREAMS, "kernels_per_tick": int(per_tick),
+            "device_us_per_batch": dev_us, "frames_per_s_device": STREAMS / dev_us * 1e6,
+            "graph_replay_plus_sync": pct(lat_graph), "host_buffer_call": pct(lat_host),
+            "note": "device = CUDA-graph replays back to back (events); graph_replay_plus_sync = one replay + stream sync seen "
+                    "from the host; host_buffer_call = fftl_stream_push with pinned host buffers (H2D + tick + D2H + sync)"}
 
 
 def run_reference(args, rank, world):
@@ -167,6 +419,7 @@ def main():
     ap.add_argument("--seconds", type=int, default=SECONDS, help=argparse.SUPPRESS)
     ap.add_argument("--no-cpu-baseline", action="store_true", help=argparse.SUPPRESS)
     ap.add_argument("--no-e2e", action="store_true", help=argparse.SUPPRESS)
+    ap.add_argument("--no-extras", action="store_true", help=argparse.SUPPRESS)  # profiling runs: skip sharded / sustained / latency
     args = ap.parse_args()
     rank = int(os.environ.get("RANK", "0"))
     world = int(os.environ.get("WORLD_SIZE", "1"))
@@ -278,15 +531,22 @@ def main():
             e2e["host_affinity"] = numa
         h_pcm.free(); h_bars.free(); h_beat.free()
 
-    # ---------------- CPU baseline beside it (rank 0, N=1 only) ----------------
+    # ---------------- sustained / sharded job / streaming latency ----------------
+    sustained = sharded = latency = None
+    if not args.no_extras:
+        sustained = sustained_leg(sp, pcm, bars, beat, dev, local_rank, frames_per_step, world, barrier, max_over_ranks)
+    del pcm, bars, beat
+    torch.cuda.empty_cache()
+    if not args.no_extras:
+        sharded = sharded_leg(F, sp, dev, rank, world, barrier, max_over_ranks, max(3, min(args.steps, 10)))
+        if rank == 0:
+            latency = latency_leg(F, dev)
+        barrier()
+
+    # ---------------- CPU baselines beside it (rank 0, N=1 only) ----------------
     cpu = None
     if rank == 0 and world == 1 and not args.no_cpu_baseline:
-        O, ocfg, cpcm, threads, want = cpu_leg(None)
-        cframes = CHANNELS * O.num_frames(ocfg, cpcm.shape[1])
-        sec, _ = O.port_run(ocfg, cpcm, threads=threads, want_i32=False)
-        cpu = {"value": cframes / sec, "unit": "frames/s", "cores": threads, "kind": "port",
-               "sample": "first %d s of the same workload (%d frames), fp32 port of the reference chain + fftwf-shim" % (want, cframes),
-               "seconds": sec}
+        cpu = cpu_baselines()
 
     if rank == 0:
         peaks, how = measured_peaks()
@@ -294,11 +554,19 @@ def main():
         flops = FLOPS_PER_FRAME * frames_per_launch
         achieved_tf = flops / (bars_kernel_ms * 1e-3) / 1e12
         achieved_gbs = BYTES_PER_FRAME * frames_per_launch / (bars_kernel_ms * 1e-3) / 1e9
-        traffic = None
+        # dram bytes per launch come from an `ncu --set full` capture (never measured under the bench itself); the
+        # record is stamped with a hash of the kernel sources it was taken from, and a stale one is not reported
+        traffic, traffic_note = None, "no capture"
         tp = os.path.join(ROOT, "profiles", "traffic.json")
         if os.path.exists(tp):
+            from fft_lines_b200.build import kernel_source_hash
             with open(tp) as f:
-                traffic = json.load(f).get("stft_bars_dram_bytes_per_launch")
+                tj = json.load(f)
+            if tj.get("kernel_source_hash") == kernel_source_hash():
+                traffic, traffic_note = tj.get("stft_bars_dram_bytes_per_launch"), "from %s" % tj.get("source")
+            else:
+                traffic_note = "stale: %s was captured from other kernel sources (hash %s, now %s)" % (
+                    tj.get("source"), tj.get("kernel_source_hash"), kernel_source_hash())
         roof = {
             "bound": "fp32", "kernel": "stft_bars_rdif_kernel<4096> (fast path; generic fallback: stft_bars_kernel<N>)",
             "achieved": achieved_tf, "peak": fp32_peak, "unit": "TFLOP/s", "frac": achieved_tf / fp32_peak,
@@ -308,7 +576,7 @@ def main():
             "kernel_ms": bars_kernel_ms,
             "hbm": {"achieved": achieved_gbs, "peak": peaks["hbm_gbs"], "unit": "GB/s",
                     "frac": achieved_gbs / peaks["hbm_gbs"], "bytes_per_frame": BYTES_PER_FRAME, "of": how},
-            "traffic": traffic,
+            "traffic": traffic, "traffic_note": traffic_note,
         }
         line = {
             "metric": "stft_frames_per_s", "value": value, "unit": "frames/s", "n_gpus": world, "steps": args.steps,
@@ -319,6 +587,7 @@ def main():
                        "sharding": "one batch per GPU, no data-path collective",
                        "l2": "input %d MB per step > 126 MB L2, no flush needed" % (CHANNELS * S * 2 // 1000000)},
             "clocks": clocks, "e2e": e2e, "gpu_launches": int(launches) * world, "roofline": roof, "cpu_baseline": cpu,
+            "sharded": sharded, "sustained": sustained, "latency": latency,
         }
         print(json.dumps(line), flush=True)
     sp.close()

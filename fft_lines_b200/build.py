@@ -22,6 +22,17 @@ HEADERS = ["kernels.cuh", "device_common.cuh", "fft_device.cuh", "stft_rdif.cuh"
            "../../include/fft_calculate.h", "../../include/beatDetector.h", "../../include/fftl_complex.h"]
 
 
+def kernel_source_hash():
+    """Short hash of the sources the dominant kernel is built from: profiles/traffic.json is stamped with it so that
+    bench.py can tell a capture of other code from a current one."""
+    import hashlib
+    h = hashlib.sha256()
+    for f in ("stft_rdif.cuh", "fft_device.cuh", "device_common.cuh", "rdif_launch.cu", "rdif_launch.h"):
+        with open(os.path.join(CSRC, f), "rb") as fh:
+            h.update(fh.read())
+    return h.hexdigest()[:16]
+
+
 def nvcc_path():
     for cand in (os.environ.get("NVCC"), shutil.which("nvcc"), "/usr/local/cuda/bin/nvcc"):
         if cand and os.path.exists(cand):
@@ -37,8 +48,11 @@ def needs_build():
     return any(os.path.getmtime(f) > t for f in files)
 
 
-def build(force=False, verbose=False, extra=(), out=None):
-    """out: alternative output path (developer A/B builds with extra -D flags)."""
+def build(force=False, verbose=False, extra=(), out=None, dev=False):
+    """out: alternative output path (developer A/B builds with extra -D flags); dev: -DFFTL_DEV (environment knobs of
+    the host path, never in the shipped library)."""
+    if dev:
+        extra = tuple(extra) + ("-DFFTL_DEV",)
     if out is None and not force and not needs_build():
         return LIB
     import tempfile
@@ -72,5 +86,8 @@ def build(force=False, verbose=False, extra=(), out=None):
 
 
 if __name__ == "__main__":
-    build(force="--force" in sys.argv, verbose="-v" in sys.argv)
-    print(LIB)
+    if "--dev" in sys.argv:
+        print(build(force=True, verbose="-v" in sys.argv, dev=True, out=os.path.join(HERE, "libfftlines_cuda_dev.so")))
+    else:
+        build(force="--force" in sys.argv, verbose="-v" in sys.argv)
+        print(LIB)

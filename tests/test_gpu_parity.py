@@ -244,7 +244,8 @@ def test_fast_path_variants_both_sizes(oracle, lib, n):
         with lib.BatchedSpectrum(cfg) as sp:
             part = sp.run(pcm, 33, 140)
             fast = sp.fast_launch_count
-            assert fast > 0
+            # (a bar set whose tables do not fit beside the slots at this CTA count runs the generic kernel anyway)
+            assert fast > 0 or cfg.bars > 256
             sp.set_kernel(_capi.KERNEL_GENERIC)
             gen = sp.run(pcm)
             assert sp.fast_launch_count == fast

@@ -247,3 +247,25 @@ def test_validation_and_empty(oracle):
     assert oracle.num_frames(c, 2047) == 0 and oracle.num_frames(c, 2048) == 1 and oracle.num_frames(c, 2048 + 511) == 1
     out = oracle.stft(c, np.zeros((2, 100), np.int16))
     assert out["bars"].shape == (2, 0, 100)
+
+
+@pytest.mark.parametrize("provider", ["scipy", "torch"])
+def test_library_fft_chain_matches_oracle(oracle, provider):
+    """oracle/numpy_chain.py (the `pocketfft` / `torch.fft` CPU baseline lines of bench.py) computes the same chain:
+    float bars within 1e-4 of the frame maximum of the fp64 oracle, integer beat stages exact when replayed."""
+    from oracle import numpy_chain as NC
+    from helpers import assert_bars_close, _peak_possible, TEMPO_REL
+    cfg = oracle.extended_config(4096, 512, 200)
+    pcm = oracle.synth_pcm(2, 4096 + 699 * 512)
+    got = NC.run(oracle, cfg, pcm, provider=provider, block=256)
+    ref = oracle.stft(cfg, pcm)
+    assert_bars_close(got["bars"], ref["bars_f64"], provider)
+    assert np.abs(got["w"] - ref["beat"]["w"]).max() <= 1 and np.abs(got["bass"] - ref["beat"]["bass"]).max() <= 1
+    for ch in range(2):
+        rep = oracle.beat_replay(cfg, got["w"][ch].astype(np.int32), got["bass"][ch].astype(np.int32))
+        for k in ("thr", "beat_value", "flag"):
+            assert (rep[k] == got[k][ch]).all(), k
+        differ = np.nonzero(rep["peak_index"] != got["peak_index"][ch])[0]
+        mag, norm = oracle.tempo_mag_replay(got["bass"][ch].astype(np.int32))
+        for f in differ:
+            assert _peak_possible(mag[f], 1.0 + TEMPO_REL * norm[f], int(got["peak_index"][ch][f])), f

@@ -80,6 +80,9 @@ for name, e in summary.items():
             return v * {"byte": 1, "Kbyte": 1e3, "Mbyte": 1e6, "Gbyte": 1e9}[u]
         t = mb(e["dram__bytes_read.sum"]) + mb(e["dram__bytes_write.sum"])
         with open(os.path.join(out_dir, "traffic.json"), "w") as f:
-            json.dump({"stft_bars_dram_bytes_per_launch": t, "source": "profiles/%s_ncu_full.md" % tag, "kernel": name}, f, indent=1)
+            sys.path.insert(0, os.path.dirname(os.path.dirname(os.path.abspath(__file__))))
+            from fft_lines_b200.build import kernel_source_hash
+            json.dump({"stft_bars_dram_bytes_per_launch": t, "source": "profiles/%s_ncu_full.md" % tag, "kernel": name,
+                       "kernel_source_hash": kernel_source_hash()}, f, indent=1)
         break
 print("wrote profiles/%s_*" % tag)

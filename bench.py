@@ -281,13 +281,13 @@ def sharded_leg(F, sp, dev, rank, world, barrier, max_over_ranks, steps):
                   "bytes": int(nbytes), "gb_per_s_per_rank": nbytes / (gms * 1e-3) / 1e9}
         del allb
     frames = SHARD_CHANNELS * total_frames
-    halo = SHARD_CHANNELS * (fb - s0 // HOP) if fe > fb else 0
+    halo = int(max_over_ranks(float(SHARD_CHANNELS * (fb - s0 // HOP) if fe > fb else 0)))
     rec = {"job": "%d channels x %d s, 4096-pt Hann, hop 512, 200 bars + beat: %d frames, frame-range sharded over %d GPU(s)"
                   % (SHARD_CHANNELS, SHARD_SECONDS, frames, world),
            "api": "fftl_stft_run_device_span (each rank holds only sharding.sample_span of the PCM, generated on its own device)",
            "frames": frames, "ms_one_gpu": t1, "ms_sharded": tn, "frames_per_s": frames / (tn * 1e-3),
            "speedup": t1 / tn, "efficiency": t1 / (world * tn), "scaling": "strong",
-           "halo_frames_recomputed_per_rank": int(halo), "collective_in_path": None,
+           "halo_frames_recomputed_per_rank_max": int(halo), "collective_in_path": None,
            "bit_exact_vs_one_gpu": bool(ok_hash), "rank_boundaries_bit_exact": bool(ok_edges),
            "boundary_check": "first and last %d frames of every shard (bars and beat records) torch.equal to the single-GPU run; "
                              "order-sensitive 64-bit checksums of every whole shard equal" % EDGE,

@@ -1,0 +1,31 @@
+"""Developer timing probe of the c3 streaming tick (1024 streams x 1024-pt): device time per tick by CUDA-graph replay."""
+import sys
+sys.path.insert(0, ".")
+import torch
+import fft_lines_b200 as F
+
+STREAMS, COUNT, B = 1024, 512, 64
+dev = torch.device("cuda")
+src = torch.empty((STREAMS, COUNT), dtype=torch.int16, device=dev)
+F.synth_pcm_device(src)
+cfg3 = F.extended_config(1024, COUNT, B)
+with F.StreamingSpectrum(cfg3, STREAMS) as ss:
+    bars = torch.empty((STREAMS, B), dtype=torch.float32, device=dev)
+    beat = torch.empty((STREAMS, 8), dtype=torch.int32, device=dev)
+    st = torch.cuda.Stream()
+    with torch.cuda.stream(st):
+        for _ in range(5):
+            ss.push_device(src, bars, None, beat, stream=st)
+        st.synchronize()
+        g = torch.cuda.CUDAGraph()
+        with torch.cuda.graph(g, stream=st):
+            ss.push_device(src, bars, None, beat, stream=st)
+        for _ in range(50):
+            g.replay()
+        e0, e1 = torch.cuda.Event(enable_timing=True), torch.cuda.Event(enable_timing=True)
+        e0.record(st)
+        for _ in range(1000):
+            g.replay()
+        e1.record(st)
+        st.synchronize()
+    print("%.2f us per tick (device, graph replay back to back)" % e0.elapsed_time(e1))

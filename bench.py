@@ -529,6 +529,30 @@ def main():
                "api": "fftl_stft_run (host int16 PCM -> host float bars + beat records, pinned buffers)"}
         if numa:
             e2e["host_affinity"] = numa
+        # What the host <-> device links of this box allow for exactly these buffers, with every rank copying at once:
+        # the step's input H2D and its outputs D2H as two bare concurrent copies (no kernels, no chunking).  The
+        # end-to-end path cannot beat this; `frac_of_link_ceiling` says how close it gets at this N.
+        s_in, s_out = torch.cuda.Stream(dev), torch.cuda.Stream(dev)
+        hb_t, hbeat_t = torch.from_numpy(h_bars.array), torch.from_numpy(h_beat.array.view(np.int32).reshape(CHANNELS, nf, -1))
+
+        def raw_copies():
+            with torch.cuda.stream(s_in):
+                pcm.copy_(pin_t, non_blocking=True)
+            with torch.cuda.stream(s_out):
+                hb_t.copy_(bars, non_blocking=True)
+                hbeat_t.copy_(beat, non_blocking=True)
+        raw_copies()
+        barrier()
+        t0 = time.perf_counter()
+        for _ in range(3):
+            raw_copies()
+        barrier()
+        dt_raw = max_over_ranks(time.perf_counter() - t0) / 3
+        moved = e2e["h2d_bytes_per_step"] + e2e["d2h_bytes_per_step"]
+        e2e["link_ceiling"] = {"ms_per_step": 1e3 * dt_raw, "value": world * frames_per_step / dt_raw, "unit": "frames/s",
+                               "aggregate_gb_per_s": world * moved / dt_raw / 1e9, "per_gpu_gb_per_s": moved / dt_raw / 1e9,
+                               "what": "this step's H2D and D2H as two bare concurrent pinned copies on every rank at once"}
+        e2e["frac_of_link_ceiling"] = e2e["value"] / e2e["link_ceiling"]["value"]
         h_pcm.free(); h_bars.free(); h_beat.free()
 
     # ---------------- sustained / sharded job / streaming latency ----------------

@@ -376,31 +376,47 @@ extern "C" int fftl_stft_create(const fftl_config* cfg, int device, fftl_stft** 
         H_TRY(cudaMemcpy(h->d_sg, sg.data(), sizeof(float) * m * m, cudaMemcpyHostToDevice));
     }
     {
-        // balanced binning: every bar is cut into segments of at most 8 bins that never cross a multiple
-        // of 16 (so a segment is contiguous in the padded magnitude array); partial sums are combined in a
-        // fixed order, which keeps the result deterministic
-        const int L = 8;
-        std::vector<int> seg_lo, seg_hi, bar_seg0(B + 1);
+        // balanced binning: every DISTINCT bin range (the low log-frequency bars repeat ranges) is cut into segments of
+        // at most L bins that never cross a multiple of 16 (so a segment is contiguous in the padded magnitude
+        // array); a bar adds up its range's segment sums in a fixed order, which keeps the result deterministic.
+        // L is the smallest of 8, 12, 16 for which the fast kernel's segment phase is ONE pass over its threads
+        // (a second pass costs a full shared-memory round trip per tile: 3.6 % of the c2 kernel).
+        const int fast_threads = n / 16 > 512 ? 512 : n / 16; // RdifShape::THREADS
+        std::vector<int> seg_lo, seg_hi, bar_seg0(B + 1);     // bar_seg0[b] = first segment | segments << 16
         std::vector<float> bar_inv(B);
-        for (int b = 0; b < B; b++) {
-            bar_seg0[b] = (int)seg_lo.size();
-            for (int k = lo[b]; k < hi[b];) {
-                int e = k + L < hi[b] ? k + L : hi[b];
-                int block_end = (k / 16 + 1) * 16;
-                if (e > block_end) e = block_end;
-                seg_lo.push_back(k);
-                seg_hi.push_back(e);
-                k = e;
+        int max_per_bar = 0;
+        for (int L = 8; L <= 16; L += 4) {
+            seg_lo.clear();
+            seg_hi.clear();
+            max_per_bar = 0;
+            for (int b = 0; b < B; b++) {
+                if (b > 0 && lo[b] == lo[b - 1] && hi[b] == hi[b - 1]) { // same range as the bar before: share its segments
+                    bar_seg0[b] = bar_seg0[b - 1];
+                    continue;
+                }
+                const int first = (int)seg_lo.size();
+                for (int k = lo[b]; k < hi[b];) {
+                    int e = k + L < hi[b] ? k + L : hi[b];
+                    int block_end = (k / 16 + 1) * 16;
+                    if (e > block_end) e = block_end;
+                    seg_lo.push_back(k);
+                    seg_hi.push_back(e);
+                    k = e;
+                }
+                const int cnt = (int)seg_lo.size() - first;
+                bar_seg0[b] = first | (cnt << 16);
+                max_per_bar = cnt > max_per_bar ? cnt : max_per_bar;
             }
-            bar_inv[b] = 1.0f / (float)(hi[b] - lo[b]);
+            if ((int)seg_lo.size() <= fast_threads) break;
         }
-        bar_seg0[B] = (int)seg_lo.size();
+        for (int b = 0; b < B; b++) bar_inv[b] = 1.0f / (float)(hi[b] - lo[b]);
+        bar_seg0[B] = 0;
         h->nseg = (int)seg_lo.size();
         h->mag_bins = cfg->bass_bin + 1;
         for (int b = 0; b < B; b++) h->mag_bins = hi[b] > h->mag_bins ? hi[b] : h->mag_bins;
         // work list of the segment sums in bin order, packed for the fast kernel
         std::vector<int> packed(h->nseg);
-        h->seg_packable = h->nseg < (1 << 14);
+        h->seg_packable = h->nseg < (1 << 13) && max_per_bar < (1 << 15);
         for (int i = 0; i < h->nseg; i++) {
             const int k = i, pl = pad_index(seg_lo[k]);
             if (pl >= (1 << 14)) h->seg_packable = false;

@@ -40,7 +40,7 @@ struct RdifParams {
     const float2* tw;           // W_n^m
     const float2* twm;          // W_M^m  (sub-transform twiddles)
     const int* seg_packed;      // [nseg] work list of the segment sums, longest first (see rdif_segment_sums)
-    const int* bar_seg0;        // [bars+1] first segment of each bar
+    const int* bar_seg0;        // [bars+1] first segment of the bar's bin range | number of segments << 16
     const float* bar_inv;       // 1 / (hi - lo)
     const float* sg;
     float* bars;
@@ -248,10 +248,10 @@ struct TileCursor {
     __device__ __forceinline__ long long first_frame(const RdifParams& p, int F) const { return p.frame0 + (long long)tic * F; }
 };
 
-// Work-list entry of the segment sums: padded first bin (14 bits) | length 1..8 (4 bits) | segment number (14 bits).
+// Work-list entry of the segment sums: padded first bin (14 bits) | length 1..16 (5 bits) | segment number (13 bits).
 // The list stays in bin order: neighbouring lanes then read neighbouring magnitudes, which is conflict-free
 // (sorting it by length was measured: 5 % slower from bank conflicts).
-#define FFTL_SEG_PACK(padded_lo, cnt, idx) ((padded_lo) | ((cnt) << 14) | ((idx) << 18))
+#define FFTL_SEG_PACK(padded_lo, cnt, idx) ((padded_lo) | ((cnt) << 14) | ((idx) << 19))
 
 template <int F, int MAGS, int K> __device__ __forceinline__ void seg_steps(const float2* m0, int cnt, float* acc)
 {
@@ -277,19 +277,18 @@ __device__ __forceinline__ void rdif_segment_sums(const int* t_seg, const float2
     for (int base = 0; base < nseg; base += nthreads) {
         const int sgi = base + t;
         const int sd = sgi < nseg ? t_seg[sgi] : 0;
-        const int cnt = (sd >> 14) & 15;
+        const int cnt = (sd >> 14) & 31;
         const float2* m0 = mags + (sd & 0x3fff);
         float acc[F];
 #pragma unroll
         for (int f = 0; f < F; f++) acc[f] = 0.0f;
-#if defined(FFTL_SEG_FIXED8)
-        seg_steps<F, MAGS, 8>(m0, cnt, acc);
-#else
-        // the low bars are 1-2 bins wide: their warps take the short form
-        if (__reduce_max_sync(0xffffffffu, cnt) <= 2) seg_steps<F, MAGS, 2>(m0, cnt, acc);
-        else seg_steps<F, MAGS, 8>(m0, cnt, acc);
-#endif
-        if (cnt) FrameVec<F>::store(segsum + (int)((unsigned)sd >> 18) * F, acc);
+        // the low bars are 1-2 bins wide: their warps take the short form; segments longer than 8 bins exist only
+        // where the host needed them to fit the work list into one pass
+        const int longest = __reduce_max_sync(0xffffffffu, cnt);
+        if (longest <= 2) seg_steps<F, MAGS, 2>(m0, cnt, acc);
+        else if (longest <= 8) seg_steps<F, MAGS, 8>(m0, cnt, acc);
+        else seg_steps<F, MAGS, 16>(m0, cnt, acc);
+        if (cnt) FrameVec<F>::store(segsum + (int)((unsigned)sd >> 19) * F, acc);
     }
 }
 
@@ -958,7 +957,7 @@ __global__ void __launch_bounds__(RdifShape<N, F>::THREADS, MINB) stft_bars_rdif
         rdif_segment_sums<F, MAGS>(t_seg, mags, segsum, p.nseg, t, THREADS);
         __syncthreads();
         for (int b = t; b < B; b += THREADS) {
-            const int a = t_bar0[b], e = t_bar0[b + 1];
+            const int a = t_bar0[b] & 0xffff, e = a + (t_bar0[b] >> 16); // the bar's range: first segment, count
             float acc[F];
             FrameVec<F>::load(segsum + a * F, acc);
             for (int k = a + 1; k < e; k++) {

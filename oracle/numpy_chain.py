@@ -115,3 +115,42 @@ def run(O, cfg, pcm, provider="scipy", workers=None, block=512):
         bv = np.where(np.isfinite(q) & (np.abs(q) < 2.0 ** 31), np.trunc(q), -2.0 ** 31).astype(np.int64)
     return {"bars": bars, "w": w, "thr": thr, "beat_value": bv, "flag": ((thr > 0) & (w > thr)).astype(np.int64),
             "bass": bass, "peak_index": peak, "workers": workers}
+
+
+def fft_only(cfg, pcm, provider="scipy", workers=None, block=512):
+    """Only the windowed real FFTs of every frame (no magnitudes, bins, smoothing or beat stages), blocks of frames over
+    all cores: an upper bound for ANY CPU chain built on this FFT.  Returns (seconds, frames, workers)."""
+    import os
+    import time
+    from concurrent.futures import ThreadPoolExecutor
+    n, hop = cfg.n, cfg.hop
+    ch, S = pcm.shape
+    F = (S - n) // hop + 1
+    if not workers or workers < 1:
+        workers = len(os.sched_getaffinity(0))
+    win = (0.5 - 0.5 * np.cos(2 * np.pi * np.arange(n) / n)).astype(np.float32)
+    if provider == "torch":
+        import torch
+        torch.set_num_threads(1)
+        twin = torch.from_numpy(win)
+
+        def one(x):
+            return torch.fft.rfft(torch.from_numpy(np.ascontiguousarray(x)).float() * twin, dim=1)
+    else:
+        import scipy.fft as sfft
+
+        def one(x):
+            return sfft.rfft(x.astype(np.float32) * win, axis=1)
+
+    def job(cf):
+        c, f0 = cf
+        frames = np.lib.stride_tricks.as_strided(pcm[c], shape=(F, n), strides=(hop * 2, 2), writeable=False)
+        one(frames[f0:f0 + block])
+
+    jobs = [(c, f0) for c in range(ch) for f0 in range(0, F, block)]
+    with ThreadPoolExecutor(max_workers=workers) as pool:
+        list(pool.map(job, jobs[:workers]))  # warm-up
+        t0 = time.perf_counter()
+        list(pool.map(job, jobs))
+        dt = time.perf_counter() - t0
+    return dt, ch * F, workers

@@ -2,6 +2,7 @@
 // (-DFFTL_RDIF_HOPQ=0|1|2|4; see rdif_launch.h).
 #include <cuda_runtime.h>
 #include "rdif_launch.h"
+#include "stft_rdif_tm.cuh"
 
 #ifndef FFTL_RDIF_HOPQ
 #error "compile with -DFFTL_RDIF_HOPQ=0|1|2|4"
@@ -19,6 +20,23 @@ static cudaError_t launch_rdif(int num_sms, RdifParams p, int channels, cudaStre
     constexpr int MINB = N >= 8192 ? 1 : N == 4096 ? 2 : (N == 2048 ? 4 : 8);
     constexpr bool RESIDENT = N != 16384; // two columns per thread at N = 16384: per-column constants are reloaded
     using Sh = RdifShape<N, F>;
+#ifndef FFTL_NO_TM
+    // N = 4096 with shared samples: three CTAs per SM with the per-thread constants in tensor memory (stft_rdif_tm.cuh)
+    if constexpr (N == 4096 && F == 4 && HOPQ > 0 && ROWS < 8) {
+        if (RdifTmShape::fits(p.bars_n, p.nseg, p.sg_half, ROWS)) {
+            if (!rdif_set_tiles(p, channels, F, HOPQ, N)) return cudaErrorNotSupported;
+            if (p.total_tiles <= 0) return cudaSuccess;
+            const size_t smem_tm = RdifTmShape::smem_bytes(p.bars_n, p.nseg, p.sg_half);
+            auto kern_tm = stft_bars_rdif_tm_kernel<HOPQ, WIN, SGW, ROWS>;
+            cudaError_t e = cudaFuncSetAttribute(kern_tm, cudaFuncAttributeMaxDynamicSharedMemorySize, (int)smem_tm);
+            if (e != cudaSuccess) return e;
+            long long grid = (long long)RdifTmShape::MINB * num_sms;
+            if (grid > p.total_tiles) grid = p.total_tiles;
+            kern_tm<<<(unsigned)grid, RdifTmShape::THREADS, smem_tm, st>>>(p);
+            return cudaGetLastError();
+        }
+    }
+#endif
     size_t smem = Sh::smem_bytes(p.bars_n, p.nseg, p.sg_half, ROWS);
     if ((smem + 1024) * (MINB <= 2 ? MINB : MINB - 1) > 228 * 1024) return cudaErrorNotSupported;
     if (!rdif_set_tiles(p, channels, F, HOPQ, N)) return cudaErrorNotSupported;

@@ -1,0 +1,370 @@
+// stft_rdif_tm.cuh -- the N = 4096 fast path with its per-thread constants parked in tensor memory (sm_100a).
+//
+// stft_bars_rdif_kernel<4096, ...> (stft_rdif.cuh) keeps 62 per-thread constants in registers for the whole
+// tile loop (window column, pass-A twiddles, pass-C twiddles): 127 registers, two CTAs of 256 threads per SM,
+// and the kernel is bound by warp latency at 16 warps per SM, not by issue slots.  Here the same arithmetic
+// runs with THREE CTAs per SM (24 warps, <= 85 registers):
+//   * the constants live in TMEM (Blackwell's 256 KB per-SM tensor memory, 512 columns x 128 lanes x 32 bit):
+//     every warp owns 64 columns of its 32-lane quarter, written once with tcgen05.st; a phase fetches the
+//     32 values it needs with ONE tcgen05.ld (pass A: window column + W_N^(t k0); pass B/C: W_256^(j r)),
+//     so a constant costs no register outside its phase and no shared-memory or L1 traffic;
+//   * the magnitudes overlay the first frame pair's slots (dead once every warp is past pass B/C of that
+//     pair) and the segment sums sit behind them, so a CTA needs 76 KB of shared memory instead of 103 KB.
+// Same results bit for bit as stft_bars_rdif_kernel (same operations in the same order); tests compare both
+// with the generic kernel and the oracle.  What the reference does per tick: fft_lines/fft_lines.c:190-208, :281.
+#pragma once
+#include "stft_rdif.cuh"
+
+namespace fftl {
+
+__device__ __forceinline__ uint32_t smem_addr_u32(const void* p) { return (uint32_t)__cvta_generic_to_shared(p); }
+
+// 128 columns of tensor memory for this CTA (one warp calls; the address lands in *holder)
+__device__ __forceinline__ void tmem_alloc_128(uint32_t* holder)
+{
+    asm volatile("tcgen05.alloc.cta_group::1.sync.aligned.shared::cta.b32 [%0], 128;" ::"r"(smem_addr_u32(holder)) : "memory");
+    asm volatile("tcgen05.relinquish_alloc_permit.cta_group::1.sync.aligned;" ::: "memory");
+}
+__device__ __forceinline__ void tmem_free_128(uint32_t taddr) { asm volatile("tcgen05.dealloc.cta_group::1.sync.aligned.b32 %0, 128;" ::"r"(taddr) : "memory"); }
+
+// 32 consecutive columns of this thread's TMEM lane <- v[0..31]
+__device__ __forceinline__ void tmem_st32(uint32_t taddr, const float* v)
+{
+    asm volatile(
+        "tcgen05.st.sync.aligned.32x32b.x32.b32 [%0], {%1, %2, %3, %4, %5, %6, %7, %8, %9, %10, %11, %12, %13, %14, %15, %16, "
+        "%17, %18, %19, %20, %21, %22, %23, %24, %25, %26, %27, %28, %29, %30, %31, %32};" ::"r"(taddr),
+        "f"(v[0]), "f"(v[1]), "f"(v[2]), "f"(v[3]), "f"(v[4]), "f"(v[5]), "f"(v[6]), "f"(v[7]), "f"(v[8]), "f"(v[9]), "f"(v[10]), "f"(v[11]),
+        "f"(v[12]), "f"(v[13]), "f"(v[14]), "f"(v[15]), "f"(v[16]), "f"(v[17]), "f"(v[18]), "f"(v[19]), "f"(v[20]), "f"(v[21]), "f"(v[22]),
+        "f"(v[23]), "f"(v[24]), "f"(v[25]), "f"(v[26]), "f"(v[27]), "f"(v[28]), "f"(v[29]), "f"(v[30]), "f"(v[31])
+        : "memory");
+}
+__device__ __forceinline__ void tmem_wait_st() { asm volatile("tcgen05.wait::st.sync.aligned;" ::: "memory"); }
+
+// v[0..31] <- 32 consecutive columns of this thread's TMEM lane; returns when the values have arrived
+__device__ __forceinline__ void tmem_ld32(uint32_t taddr, float* v)
+{
+    asm volatile(
+        "tcgen05.ld.sync.aligned.32x32b.x32.b32 {%0, %1, %2, %3, %4, %5, %6, %7, %8, %9, %10, %11, %12, %13, %14, %15, "
+        "%16, %17, %18, %19, %20, %21, %22, %23, %24, %25, %26, %27, %28, %29, %30, %31}, [%32];\n\t"
+        "tcgen05.wait::ld.sync.aligned;"
+        : "=f"(v[0]), "=f"(v[1]), "=f"(v[2]), "=f"(v[3]), "=f"(v[4]), "=f"(v[5]), "=f"(v[6]), "=f"(v[7]), "=f"(v[8]), "=f"(v[9]), "=f"(v[10]),
+          "=f"(v[11]), "=f"(v[12]), "=f"(v[13]), "=f"(v[14]), "=f"(v[15]), "=f"(v[16]), "=f"(v[17]), "=f"(v[18]), "=f"(v[19]), "=f"(v[20]),
+          "=f"(v[21]), "=f"(v[22]), "=f"(v[23]), "=f"(v[24]), "=f"(v[25]), "=f"(v[26]), "=f"(v[27]), "=f"(v[28]), "=f"(v[29]), "=f"(v[30]),
+          "=f"(v[31])
+        : "r"(taddr)
+        : "memory");
+}
+
+
+// v[0..15] <- 16 consecutive columns of this thread's TMEM lane, asynchronously: tmem_wait16(v) before any use
+__device__ __forceinline__ void tmem_ld16_async(uint32_t taddr, float* v)
+{
+    asm volatile(
+        "tcgen05.ld.sync.aligned.32x32b.x16.b32 {%0, %1, %2, %3, %4, %5, %6, %7, %8, %9, %10, %11, %12, %13, %14, %15}, [%16];"
+        : "=f"(v[0]), "=f"(v[1]), "=f"(v[2]), "=f"(v[3]), "=f"(v[4]), "=f"(v[5]), "=f"(v[6]), "=f"(v[7]), "=f"(v[8]), "=f"(v[9]), "=f"(v[10]),
+          "=f"(v[11]), "=f"(v[12]), "=f"(v[13]), "=f"(v[14]), "=f"(v[15])
+        : "r"(taddr)
+        : "memory");
+}
+// the wait names the registers as in/out operands so that no use of them can be scheduled in front of it
+__device__ __forceinline__ void tmem_wait16(float* v)
+{
+    asm volatile("tcgen05.wait::ld.sync.aligned;"
+                 : "+f"(v[0]), "+f"(v[1]), "+f"(v[2]), "+f"(v[3]), "+f"(v[4]), "+f"(v[5]), "+f"(v[6]), "+f"(v[7]), "+f"(v[8]), "+f"(v[9]), "+f"(v[10]),
+                   "+f"(v[11]), "+f"(v[12]), "+f"(v[13]), "+f"(v[14]), "+f"(v[15])
+                 :
+                 : "memory");
+}
+
+// TileCursor (stft_rdif.cuh) without the two 64-bit per-advance steps held in registers: they are recomputed from the
+// launch parameters (constant bank) once per tile.  Planar PCM only (sample_stride 1).
+struct TileCursorLean {
+    int left, tic, ch;
+    const int16_t* xp;
+    long long o0;
+    __device__ __forceinline__ void init(const RdifParams& p, long long first, long long stride, int F)
+    {
+        left = first < p.total_tiles ? (int)((p.total_tiles - first + stride - 1) / stride) : 0;
+        ch = (int)(first / p.tiles_per_channel);
+        tic = (int)(first - (long long)ch * p.tiles_per_channel);
+        const long long f0 = p.frame0 + (long long)tic * F;
+        xp = p.pcm + (long long)ch * p.channel_stride + f0 * p.hop;
+        o0 = ((long long)ch * p.nf_emit + (f0 - p.frame_emit)) * p.bars_n;
+    }
+    __device__ __forceinline__ void advance(const RdifParams& p, int stride, int F)
+    {
+        left--;
+        tic += stride;
+        xp += (long long)(stride * F) * p.hop;
+        o0 += (long long)(stride * F) * p.bars_n;
+        while (tic >= (int)p.tiles_per_channel) {
+            tic -= (int)p.tiles_per_channel;
+            ch++;
+            xp += p.channel_stride - p.tiles_per_channel * F * p.hop;
+            o0 += (p.nf_emit - p.tiles_per_channel * F) * p.bars_n;
+        }
+    }
+    __device__ __forceinline__ long long first_frame(const RdifParams& p, int F) const { return p.frame0 + (long long)tic * F; }
+};
+
+struct RdifTmShape {
+    static constexpr int N = 4096, F = 4, M = 256, THREADS = 256, MINB = 3;
+    static constexpr int SLOT = padded_size(M);
+    using Sh = RdifShape<N, F>;
+    // shared memory: [32 slots] [raw bars] [tables] [tmem address]; magnitudes and segment sums overlay the first pair's slots
+    static size_t smem_bytes(int bars, int nseg, int sg_half) { return (size_t)32 * SLOT * sizeof(float2) + (size_t)bars * F * sizeof(float) + Sh::table_bytes(bars, nseg, sg_half) + 16; }
+    static bool fits(int bars, int nseg, int sg_half, int rows)
+    {
+        if (rows >= 8) return false; // bin N/2 would not fit the overlay
+        const size_t overlay = (size_t)2 * Sh::mag_stride(rows) * sizeof(float2) + (size_t)nseg * F * sizeof(float);
+        return overlay <= (size_t)16 * SLOT * sizeof(float2) && (smem_bytes(bars, nseg, sg_half) + 1024) * MINB <= 228 * 1024;
+    }
+};
+
+template <int HOPQ, bool WINDOWED, int SGW, int ROWS>
+__global__ void __launch_bounds__(RdifTmShape::THREADS, RdifTmShape::MINB) stft_bars_rdif_tm_kernel(const RdifParams p)
+{
+    constexpr int N = RdifTmShape::N, F = RdifTmShape::F, M = RdifTmShape::M, SLOT = RdifTmShape::SLOT, THREADS = RdifTmShape::THREADS;
+    using Sh = RdifShape<N, F>;
+    constexpr int MAGS = Sh::mag_stride(ROWS);
+    static_assert(HOPQ == 1 || HOPQ == 2 || HOPQ == 4, "the tile's frames share their samples");
+    static_assert(ROWS >= 1 && ROWS < 8, "magnitude rows");
+    constexpr int NX = 16 + HOPQ * (F - 1);
+    constexpr int NMG = 2 * ROWS; // magnitudes a thread produces per sub-transform
+
+    extern __shared__ float2 smem[];
+    float2* slots = smem;                                        // [2 pairs][16][SLOT]
+    float2* mags = smem;                                         // [2 pairs][MAGS], over the first pair's slots
+    float* segsum = reinterpret_cast<float*>(smem + 2 * MAGS);   // [nseg][F], behind them (RdifTmShape::fits)
+    float* raw = reinterpret_cast<float*>(smem + 32 * SLOT);     // [bars][F]
+    int* t_seg = reinterpret_cast<int*>(raw + p.bars_n * F);     // [nseg] FFTL_SEG_PACK work list
+    int* t_bar0 = t_seg + p.nseg;                                // [bars+1]
+    float* t_inv = reinterpret_cast<float*>(t_bar0 + p.bars_n + 1); // [bars]
+    float* t_sg = t_inv + p.bars_n;                              // [(2w+1)^2]
+    uint32_t* tm_holder = reinterpret_cast<uint32_t*>(t_sg + (2 * p.sg_half + 1) * (2 * p.sg_half + 1));
+    const int t = threadIdx.x;
+    const int B = p.bars_n;
+    const int j = t & 15;   // lane within the sub-transform
+    const int hw = t >> 4;  // which slot of a frame pair this half-warp owns
+    const int warp = t >> 5;
+
+    if (warp == 0) tmem_alloc_128(tm_holder);
+    for (int i = t; i < p.nseg; i += THREADS) t_seg[i] = __ldg(p.seg_packed + i);
+    for (int i = t; i <= p.bars_n; i += THREADS) t_bar0[i] = __ldg(p.bar_seg0 + i);
+    for (int i = t; i < p.bars_n; i += THREADS) t_inv[i] = __ldg(p.bar_inv + i);
+    for (int i = t; i < (2 * p.sg_half + 1) * (2 * p.sg_half + 1); i += THREADS) t_sg[i] = p.sg ? __ldg(p.sg + i) : 0.0f;
+    asm volatile("tcgen05.fence::before_thread_sync;" ::: "memory");
+    __syncthreads();
+    asm volatile("tcgen05.fence::after_thread_sync;" ::: "memory");
+    const uint32_t tm_base = *tm_holder;
+    // this warp's 64 columns of its 32-lane quarter: [0, 32) window column + W_N^(t k0), [32, 64) W_256^(j r)
+    const uint32_t tm = tm_base + ((uint32_t)(32 * (warp & 3)) << 16) + (uint32_t)(warp >> 2) * 64;
+    {
+        float c[32];
+#pragma unroll
+        for (int q = 0; q < 16; q++) c[q] = WINDOWED ? __ldg(p.window + t + M * q) : 1.0f;
+#pragma unroll
+        for (int k0 = 1; k0 <= 8; k0++) {
+            const float2 w = __ldg(p.tw + t * k0);
+            c[14 + 2 * k0] = w.x;
+            c[15 + 2 * k0] = w.y;
+        }
+        tmem_st32(tm, c);
+        c[30] = c[31] = 0.0f;
+#pragma unroll
+        for (int r = 1; r < 16; r++) {
+            const float2 w = __ldg(p.twm + j * r);
+            c[2 * r - 2] = w.x;
+            c[2 * r - 1] = w.y;
+        }
+        tmem_st32(tm + 32, c);
+        tmem_wait_st();
+    }
+
+    TileCursorLean cur;
+    cur.init(p, blockIdx.x, gridDim.x, F);
+    for (; cur.left > 0; cur.advance(p, gridDim.x, F)) {
+        const int16_t* xp = cur.xp + t;
+
+        // ================= pass A (both frame pairs) =================
+        float xr[NX];
+        if (cur.tic < p.tic_full) { // every sample the tile reads exists
+#pragma unroll
+            for (int r = 0; r < NX; r++) xr[r] = pcm_to_float(xp + r * M);
+        } else {
+            const long long s0 = cur.first_frame(p, F) * (long long)p.hop; // the tile's first sample
+#pragma unroll
+            for (int r = 0; r < NX; r++) xr[r] = (s0 + t + (long long)r * M < p.samples) ? pcm_to_float(xp + r * M) : 0.0f;
+        }
+#ifdef FFTL_TM_PERTILE
+        {
+            float ca[32]; // window column, W_N^(t k0)
+            tmem_ld32(tm, ca);
+#pragma unroll
+            for (int pr = 0; pr < 2; pr++) {
+                float2* ps = slots + pr * 16 * SLOT + pad_index(t);
+                float y0[2], y8[2];
+#pragma unroll
+                for (int h = 0; h < 2; h++) {
+                    const int f = 2 * pr + h;
+                    float yr[9], yi[9];
+                    real_dft16<WINDOWED>(xr + HOPQ * f, ca, yr, yi);
+                    y0[h] = yr[0];
+                    y8[h] = yr[8];
+#pragma unroll
+                    for (int k0 = 1; k0 < 8; k0++) ps[(2 * k0 + h) * SLOT] = cmul(make_float2(yr[k0], yi[k0]), make_float2(ca[14 + 2 * k0], ca[15 + 2 * k0]));
+                }
+                ps[0] = make_float2(y0[0], y0[1]);
+                ps[SLOT] = cmul(make_float2(y8[0], y8[1]), make_float2(ca[30], ca[31]));
+            }
+        }
+#else
+        // the window column and the twiddles are fetched per frame (16 registers each, live only while they are used):
+        // the window is dead after the first butterfly stage, the twiddles are asked for before it and waited for behind the DFT
+#pragma unroll
+        for (int pr = 0; pr < 2; pr++) {
+            float2* ps = slots + pr * 16 * SLOT + pad_index(t);
+            float y0[2], y8[2];
+            float2 w8;
+#pragma unroll
+            for (int h = 0; h < 2; h++) {
+                const int f = 2 * pr + h;
+                float yr[9], yi[9];
+                float cw[16], ct[16];
+                if (WINDOWED) tmem_ld16_async(tm, cw);
+                tmem_ld16_async(tm + 16, ct);
+                if (WINDOWED) tmem_wait16(cw);
+                real_dft16<WINDOWED>(xr + HOPQ * f, cw, yr, yi);
+                tmem_wait16(ct);
+                y0[h] = yr[0];
+                y8[h] = yr[8];
+#pragma unroll
+                for (int k0 = 1; k0 < 8; k0++) ps[(2 * k0 + h) * SLOT] = cmul(make_float2(yr[k0], yi[k0]), make_float2(ct[2 * k0 - 2], ct[2 * k0 - 1]));
+                w8 = make_float2(ct[14], ct[15]);
+            }
+            ps[0] = make_float2(y0[0], y0[1]);
+            ps[SLOT] = cmul(make_float2(y8[0], y8[1]), w8);
+        }
+#endif
+        __syncthreads();
+
+        // ================= pass B/C =================
+        float cc[32]; // W_256^(j r), r = 1..15
+        tmem_ld32(tm + 32, cc);
+        // the sub-transform of slot (pr, hw); leaves the magnitudes this thread has to store in mg[]
+        auto bc_compute = [&](const int pr, float* mg) {
+            float2* s = slots + (pr * 16 + hw) * SLOT;
+            float2 v[16];
+#pragma unroll
+            for (int r = 0; r < 16; r++) v[r] = s[pad_index(j + r * 16)];
+            radix16_fused<false>(v, nullptr);
+            __syncwarp();
+#pragma unroll
+            for (int rr = 0; rr < 16; rr++) s[pad_index(16 * j + Radix<16>::out_index(rr))] = v[rr];
+            __syncwarp();
+#pragma unroll
+            for (int r = 0; r < 16; r++) v[r] = s[pad_index(j + r * 16)];
+            {
+                float2 twc[16];
+#pragma unroll
+                for (int r = 1; r < 16; r++) twc[r] = make_float2(cc[2 * r - 2], cc[2 * r - 1]);
+                radix16_fused<true>(v, twc);
+            }
+            // v[rr] = Z[m], m = j + 16*kk, kk = out_index(rr)
+            if (hw >= 2) {
+#pragma unroll
+                for (int rr = 0; rr < 16; rr++) {
+                    const int kk = Radix<16>::out_index(rr);
+                    const int c = kk < 8 ? kk : 15 - kk; // 256-bin row of this output
+                    if (c < ROWS) mg[kk < 8 ? c : ROWS + c] = sqrtf(fmaf(v[rr].x, v[rr].x, v[rr].y * v[rr].y));
+                }
+            } else {
+                // packed slot (hw 0: residue 0, partner m' = 256-m; hw 1: residue 8, partner m' = 255-m)
+                const int src = hw ? (15 - j) : ((16 - j) & 15);
+                const bool self = (hw == 0) && (j == 0);
+#pragma unroll
+                for (int kk = 0; kk < ROWS; kk++) {
+                    const int rr = 4 * (kk & 3) + (kk >> 2);
+                    const int kp = 15 - kk, rp = 4 * (kp & 3) + (kp >> 2);
+                    float pr_ = __shfl_sync(0xffffffffu, v[rp].x, src, 16);
+                    float pi_ = __shfl_sync(0xffffffffu, v[rp].y, src, 16);
+                    if (self) {
+                        const int ks = (16 - kk) & 15, rs = 4 * (ks & 3) + (ks >> 2);
+                        pr_ = v[rs].x;
+                        pi_ = v[rs].y;
+                    }
+                    float ar = v[rr].x + pr_, ai = v[rr].y - pi_; // 2 * Xa
+                    float br = v[rr].x - pr_, bi = v[rr].y + pi_; // 2i * Xb
+                    mg[2 * kk] = 0.5f * sqrtf(fmaf(ar, ar, ai * ai));
+                    mg[2 * kk + 1] = 0.5f * sqrtf(fmaf(br, br, bi * bi));
+                }
+            }
+        };
+        auto bc_store = [&](const int pr, const float* mg) {
+            float2* mg2 = mags + pr * MAGS;
+            if (hw >= 2) {
+                // regular slot: frame h = hw&1, residue k0 = hw>>1; m < 128 is bin k0 + 16m, m >= 128 the conjugate mirror
+                const int k0 = hw >> 1;
+                float* mgf = reinterpret_cast<float*>(mg2) + (hw & 1);
+                float* lo_base = mgf + 2 * (k0 + 17 * j);                 // pad_index(k0 + 16j + 256c) = k0 + 17j + 272c
+                float* hi_base = mgf + 2 * ((16 - k0) + 17 * (15 - j));   // mirror: (16-k0) + 17(15-j) + 272c
+#pragma unroll
+                for (int c = 0; c < ROWS; c++) {
+                    lo_base[2 * 272 * c] = mg[c];
+                    hi_base[2 * 272 * c] = mg[ROWS + c];
+                }
+            } else {
+#pragma unroll
+                for (int kk = 0; kk < ROWS; kk++) {
+                    const int bin = 16 * (j + 16 * kk) + (hw ? 8 : 0);
+                    mg2[pad_index(bin)] = make_float2(mg[2 * kk], mg[2 * kk + 1]);
+                }
+            }
+        };
+        {
+            float mg0[NMG], mg1[NMG];
+            bc_compute(0, mg0);
+            __syncthreads(); // every warp is done with the first pair's slots: the magnitudes may overlay them
+            bc_store(0, mg0);
+            bc_compute(1, mg1);
+            bc_store(1, mg1);
+        }
+        __syncthreads();
+        // ================= bins -> bars, SG, outputs: every item carries the tile's F frames =================
+        rdif_segment_sums<F, MAGS>(t_seg, mags, segsum, p.nseg, t, THREADS);
+        __syncthreads();
+        for (int b = t; b < B; b += THREADS) {
+            const int a = t_bar0[b] & 0xffff, e = a + (t_bar0[b] >> 16); // the bar's range: first segment, count
+            float acc[F];
+            FrameVec<F>::load(segsum + a * F, acc);
+            for (int k = a + 1; k < e; k++) {
+                float u[F];
+                FrameVec<F>::load(segsum + k * F, u);
+#pragma unroll
+                for (int f = 0; f < F; f++) acc[f] += u[f];
+            }
+            const float inv = t_inv[b];
+#pragma unroll
+            for (int f = 0; f < F; f++) acc[f] *= inv;
+            FrameVec<F>::store(raw + b * F, acc);
+        }
+        // bass = (int)|X[bass_bin]| (beatDetector.c:53) while the magnitudes are still in place: the last F threads
+        if (p.aux_w != nullptr && t >= THREADS - F) {
+            const int f = t - (THREADS - F);
+            const long long fr = cur.first_frame(p, F) + f;
+            if (fr < p.frame_end) {
+                const float2 mb = mags[(f >> 1) * MAGS + pad_index(p.bass_bin)];
+                p.aux_bass[(long long)cur.ch * p.nf_aux + (fr - p.aux_base)] = trunc_i32((f & 1) ? mb.y : mb.x, p.strict);
+            }
+        }
+        __syncthreads();
+        if (t < 4 * F) rdif_emit_beat<F, SGW>(p, raw, t_sg, nullptr, MAGS, t, cur.ch, cur.first_frame(p, F));
+        rdif_emit_bars<F, SGW>(p, raw, t_sg, t, THREADS, cur.tic >= p.tic_emit_lo && cur.tic < p.tic_emit_hi, cur.o0, cur.first_frame(p, F));
+        // No barrier here: the next tile's pass A writes slots (and through them the overlay), which nobody reads after
+        // the barrier above; `raw` is rewritten only after four more barriers.
+    }
+    __syncthreads();
+    if (warp == 0) tmem_free_128(tm_base);
+}
+
+} // namespace fftl

@@ -107,12 +107,29 @@ struct TileCursorLean {
     __device__ __forceinline__ long long first_frame(const RdifParams& p, int F) const { return p.frame0 + (long long)tic * F; }
 };
 
+// split-phase CTA barrier on an mbarrier in shared memory (count = all threads of the CTA)
+__device__ __forceinline__ void mbar_init(uint64_t* mb, unsigned count) { asm volatile("mbarrier.init.shared::cta.b64 [%0], %1;" ::"r"(smem_addr_u32(mb)), "r"(count) : "memory"); }
+__device__ __forceinline__ void mbar_arrive(uint64_t* mb)
+{
+    asm volatile("{\n\t.reg .b64 st;\n\tmbarrier.arrive.shared::cta.b64 st, [%0];\n\t}" ::"r"(smem_addr_u32(mb)) : "memory");
+}
+__device__ __forceinline__ void mbar_wait(uint64_t* mb, unsigned parity)
+{
+    asm volatile(
+        "{\n\t.reg .pred p;\n"
+        "WAIT_%=:\n\t"
+        "mbarrier.try_wait.parity.shared::cta.b64 p, [%0], %1;\n\t"
+        "@!p bra WAIT_%=;\n\t}" ::"r"(smem_addr_u32(mb)),
+        "r"(parity)
+        : "memory");
+}
+
 struct RdifTmShape {
     static constexpr int N = 4096, F = 4, M = 256, THREADS = 256, MINB = 3;
     static constexpr int SLOT = padded_size(M);
     using Sh = RdifShape<N, F>;
     // shared memory: [32 slots] [raw bars] [tables] [tmem address]; magnitudes and segment sums overlay the first pair's slots
-    static size_t smem_bytes(int bars, int nseg, int sg_half) { return (size_t)32 * SLOT * sizeof(float2) + (size_t)bars * F * sizeof(float) + Sh::table_bytes(bars, nseg, sg_half) + 16; }
+    static size_t smem_bytes(int bars, int nseg, int sg_half) { return (size_t)32 * SLOT * sizeof(float2) + (size_t)bars * F * sizeof(float) + Sh::table_bytes(bars, nseg, sg_half) + 32; }
     static bool fits(int bars, int nseg, int sg_half, int rows)
     {
         if (rows >= 8) return false; // bin N/2 would not fit the overlay
@@ -132,7 +149,11 @@ __global__ void __launch_bounds__(RdifTmShape::THREADS, RdifTmShape::MINB) stft_
     constexpr int NX = 16 + HOPQ * (F - 1);
     constexpr int NMG = 2 * ROWS; // magnitudes a thread produces per sub-transform
 
-    extern __shared__ float2 smem[];
+    extern __shared__ float2 smem_raw[];
+    // 32-byte header at a fixed place (no address registers): split barrier between the bar sums and the next tile's pass A (8 bytes), TMEM address at byte 24
+    uint64_t* mb = reinterpret_cast<uint64_t*>(smem_raw);
+    uint32_t* tm_holder = reinterpret_cast<uint32_t*>(mb + 3);
+    float2* smem = smem_raw + 4;
     float2* slots = smem;                                        // [2 pairs][16][SLOT]
     float2* mags = smem;                                         // [2 pairs][MAGS], over the first pair's slots
     float* segsum = reinterpret_cast<float*>(smem + 2 * MAGS);   // [nseg][F], behind them (RdifTmShape::fits)
@@ -141,7 +162,6 @@ __global__ void __launch_bounds__(RdifTmShape::THREADS, RdifTmShape::MINB) stft_
     int* t_bar0 = t_seg + p.nseg;                                // [bars+1]
     float* t_inv = reinterpret_cast<float*>(t_bar0 + p.bars_n + 1); // [bars]
     float* t_sg = t_inv + p.bars_n;                              // [(2w+1)^2]
-    uint32_t* tm_holder = reinterpret_cast<uint32_t*>(t_sg + (2 * p.sg_half + 1) * (2 * p.sg_half + 1));
     const int t = threadIdx.x;
     const int B = p.bars_n;
     const int j = t & 15;   // lane within the sub-transform
@@ -149,6 +169,10 @@ __global__ void __launch_bounds__(RdifTmShape::THREADS, RdifTmShape::MINB) stft_
     const int warp = t >> 5;
 
     if (warp == 0) tmem_alloc_128(tm_holder);
+    if (t == 0) {
+        mbar_init(mb, THREADS);
+    }
+    unsigned mb_parity = 0;
     for (int i = t; i < p.nseg; i += THREADS) t_seg[i] = __ldg(p.seg_packed + i);
     for (int i = t; i <= p.bars_n; i += THREADS) t_bar0[i] = __ldg(p.bar_seg0 + i);
     for (int i = t; i < p.bars_n; i += THREADS) t_inv[i] = __ldg(p.bar_inv + i);
@@ -183,6 +207,19 @@ __global__ void __launch_bounds__(RdifTmShape::THREADS, RdifTmShape::MINB) stft_
 
     TileCursorLean cur;
     cur.init(p, blockIdx.x, gridDim.x, F);
+    // Heights of a tile are written one tile late (FFTL_TM_DEFER_EMIT): the Savitzky-Golay + store step of tile i-1 runs in
+    // the middle of pass B/C of tile i, on warps 1..7 only -- warp 0 owns the two packed slots, whose untangling costs
+    // it ~70 instructions more per frame pair than a regular slot costs the others, so the other warps would
+    // otherwise wait for it at both barriers of pass B/C; and the tile loop has one barrier and one latency-bound
+    // phase less.  Warp 0's share of that step is the band energy.
+    bool have_prev = false;
+    int prev_tic = 0, prev_ch = 0;
+    long long prev_o0 = 0;
+    auto emit_prev = [&](const int tid, const int nthr, const bool beat_lanes) {
+        const long long pf0 = p.frame0 + (long long)prev_tic * F;
+        if (beat_lanes) rdif_emit_beat<F, SGW>(p, raw, t_sg, nullptr, MAGS, t, prev_ch, pf0);
+        if (tid >= 0) rdif_emit_bars<F, SGW>(p, raw, t_sg, tid, nthr, prev_tic >= p.tic_emit_lo && prev_tic < p.tic_emit_hi, prev_o0, pf0);
+    };
     for (; cur.left > 0; cur.advance(p, gridDim.x, F)) {
         const int16_t* xp = cur.xp + t;
 
@@ -196,29 +233,10 @@ __global__ void __launch_bounds__(RdifTmShape::THREADS, RdifTmShape::MINB) stft_
 #pragma unroll
             for (int r = 0; r < NX; r++) xr[r] = (s0 + t + (long long)r * M < p.samples) ? pcm_to_float(xp + r * M) : 0.0f;
         }
-#ifdef FFTL_TM_PERTILE
-        {
-            float ca[32]; // window column, W_N^(t k0)
-            tmem_ld32(tm, ca);
-#pragma unroll
-            for (int pr = 0; pr < 2; pr++) {
-                float2* ps = slots + pr * 16 * SLOT + pad_index(t);
-                float y0[2], y8[2];
-#pragma unroll
-                for (int h = 0; h < 2; h++) {
-                    const int f = 2 * pr + h;
-                    float yr[9], yi[9];
-                    real_dft16<WINDOWED>(xr + HOPQ * f, ca, yr, yi);
-                    y0[h] = yr[0];
-                    y8[h] = yr[8];
-#pragma unroll
-                    for (int k0 = 1; k0 < 8; k0++) ps[(2 * k0 + h) * SLOT] = cmul(make_float2(yr[k0], yi[k0]), make_float2(ca[14 + 2 * k0], ca[15 + 2 * k0]));
-                }
-                ps[0] = make_float2(y0[0], y0[1]);
-                ps[SLOT] = cmul(make_float2(y8[0], y8[1]), make_float2(ca[30], ca[31]));
-            }
+        if (have_prev) { // every thread is done with the previous tile's magnitudes and segment sums
+            mbar_wait(mb, mb_parity);
+            mb_parity ^= 1u;
         }
-#else
         // the window column and the twiddles are fetched per frame (16 registers each, live only while they are used):
         // the window is dead after the first butterfly stage, the twiddles are asked for before it and waited for behind the DFT
 #pragma unroll
@@ -245,16 +263,14 @@ __global__ void __launch_bounds__(RdifTmShape::THREADS, RdifTmShape::MINB) stft_
             ps[0] = make_float2(y0[0], y0[1]);
             ps[SLOT] = cmul(make_float2(y8[0], y8[1]), w8);
         }
-#endif
-        __syncthreads();
+        __syncthreads(); // (also: the previous tile's raw bars are complete)
 
         // ================= pass B/C =================
         float cc[32]; // W_256^(j r), r = 1..15
         tmem_ld32(tm + 32, cc);
-        // the sub-transform of slot (pr, hw); leaves the magnitudes this thread has to store in mg[]
-        auto bc_compute = [&](const int pr, float* mg) {
+        // first sub-pass of slot (pr, hw) (no twiddles): radix 16 over t = j + 16 r through the slot, inputs of the second in v[]
+        auto bc_first = [&](const int pr, float2* v) {
             float2* s = slots + (pr * 16 + hw) * SLOT;
-            float2 v[16];
 #pragma unroll
             for (int r = 0; r < 16; r++) v[r] = s[pad_index(j + r * 16)];
             radix16_fused<false>(v, nullptr);
@@ -264,6 +280,9 @@ __global__ void __launch_bounds__(RdifTmShape::THREADS, RdifTmShape::MINB) stft_
             __syncwarp();
 #pragma unroll
             for (int r = 0; r < 16; r++) v[r] = s[pad_index(j + r * 16)];
+        };
+        // second sub-pass (twiddled) and the magnitudes this thread has to store, left in mg[]
+        auto bc_second = [&](float2* v, float* mg) {
             {
                 float2 twc[16];
 #pragma unroll
@@ -323,14 +342,18 @@ __global__ void __launch_bounds__(RdifTmShape::THREADS, RdifTmShape::MINB) stft_
         };
         {
             float mg0[NMG], mg1[NMG];
-            bc_compute(0, mg0);
+            float2 v[16];
+            bc_first(0, v);
+            bc_second(v, mg0);
             __syncthreads(); // every warp is done with the first pair's slots: the magnitudes may overlay them
             bc_store(0, mg0);
-            bc_compute(1, mg1);
+            if (have_prev) emit_prev(t - 32, THREADS - 32, t < 4 * F);
+            bc_first(1, v);
+            bc_second(v, mg1);
             bc_store(1, mg1);
         }
         __syncthreads();
-        // ================= bins -> bars, SG, outputs: every item carries the tile's F frames =================
+        // ================= bins -> bars: every item carries the tile's F frames =================
         rdif_segment_sums<F, MAGS>(t_seg, mags, segsum, p.nseg, t, THREADS);
         __syncthreads();
         for (int b = t; b < B; b += THREADS) {
@@ -353,16 +376,22 @@ __global__ void __launch_bounds__(RdifTmShape::THREADS, RdifTmShape::MINB) stft_
             const int f = t - (THREADS - F);
             const long long fr = cur.first_frame(p, F) + f;
             if (fr < p.frame_end) {
-                const float2 mb = mags[(f >> 1) * MAGS + pad_index(p.bass_bin)];
-                p.aux_bass[(long long)cur.ch * p.nf_aux + (fr - p.aux_base)] = trunc_i32((f & 1) ? mb.y : mb.x, p.strict);
+                const float2 mb2 = mags[(f >> 1) * MAGS + pad_index(p.bass_bin)];
+                p.aux_bass[(long long)cur.ch * p.nf_aux + (fr - p.aux_base)] = trunc_i32((f & 1) ? mb2.y : mb2.x, p.strict);
             }
         }
-        __syncthreads();
-        if (t < 4 * F) rdif_emit_beat<F, SGW>(p, raw, t_sg, nullptr, MAGS, t, cur.ch, cur.first_frame(p, F));
-        rdif_emit_bars<F, SGW>(p, raw, t_sg, t, THREADS, cur.tic >= p.tic_emit_lo && cur.tic < p.tic_emit_hi, cur.o0, cur.first_frame(p, F));
-        // No barrier here: the next tile's pass A writes slots (and through them the overlay), which nobody reads after
-        // the barrier above; `raw` is rewritten only after four more barriers.
+        prev_tic = cur.tic;
+        prev_ch = cur.ch;
+        prev_o0 = cur.o0;
+        have_prev = true;
+        // Split barrier instead of a fifth CTA barrier: the next tile's pass A writes slots, and through them the
+        // magnitudes and segment sums this phase has just read; a thread arrives here and waits only in front of its
+        // first slot store, behind the next tile's sample loads.  `raw` is read behind the next tile's first two
+        // barriers and rewritten behind its fourth.
+        mbar_arrive(mb);
     }
+    __syncthreads();
+    if (have_prev) emit_prev(t, THREADS, t < 4 * F); // the CTA's last tile
     __syncthreads();
     if (warp == 0) tmem_free_128(tm_base);
 }

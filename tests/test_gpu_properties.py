@@ -7,7 +7,7 @@ import numpy as np
 import pytest
 from hypothesis import given, settings, strategies as st
 
-from helpers import assert_bars_close, assert_int_heights, assert_peaks_explained
+from helpers import PAIR_LEAK, assert_bars_close, assert_int_heights, assert_peaks_explained
 
 pytestmark = pytest.mark.gpu
 
@@ -18,7 +18,7 @@ def _ocfg(O, cfg):
     return oc
 
 
-@settings(max_examples=12, deadline=None)
+@settings(max_examples=12, deadline=None, derandomize=True)  # the same examples in every run: a CI suite must not be a lottery
 @given(n=st.sampled_from([256, 512, 1024, 2048, 4096]), seed=st.integers(0, 2 ** 31 - 1),
        shape=st.sampled_from(["uniform", "sparse", "loud", "tiny", "square"]))
 def test_random_frames_against_the_definition(oracle, lib, n, seed, shape):
@@ -46,8 +46,29 @@ def test_random_frames_against_the_definition(oracle, lib, n, seed, shape):
     for f in range(frames):
         X = oracle.dft_naive(pcm[0, f * hop:f * hop + n].astype(np.float64))
         ref[0, f] = np.abs(X[:B]) * float(np.float32(1e-3))
-    assert_bars_close(got["bars"], ref, "n=%d %s" % (n, shape))
+    # "sparse" can produce a frame of pure digital silence next to a loud one: see assert_bars_close(pair_leak)
+    assert_bars_close(got["bars"], ref, "n=%d %s" % (n, shape), pair_leak=PAIR_LEAK if shape == "sparse" else 0.0)
     assert_int_heights(got["bars_i32"], ref.astype(np.int64).astype(np.int32), ref, "n=%d %s" % (n, shape))
+
+
+@pytest.mark.parametrize("n", [256, 512, 2048, 4096])
+def test_silent_frame_next_to_a_loud_one(oracle, lib, n):
+    """Digital silence in frame 2k, full-scale noise in frame 2k+1 (found by the random test above, seeds 1625994511 /
+    1694285286 at n = 512 / 256): the silent frame's (int) heights are exactly 0 and its float heights at most
+    PAIR_LEAK of the loud frame's maximum -- the rounding residue of the packed pair transform, not 0.0 as fftwf gives."""
+    rng = np.random.default_rng(n)
+    hop = n
+    pcm = np.zeros((1, 4 * n), np.int16)
+    pcm[0, n:2 * n] = rng.integers(-32768, 32768, n)      # frame 1 loud, frames 0, 2, 3 silent
+    B = n // 2 + 1 if n <= 2048 else 2048
+    cfg = lib.reference_config(n, hop, B, zoom=1e-3)
+    with lib.BatchedSpectrum(cfg) as sp:
+        got = sp.run(pcm, want_beat=False)
+    loud = np.abs(got["bars"][0, 1]).max()
+    assert loud > 100.0
+    assert np.abs(got["bars"][0, 0]).max() <= PAIR_LEAK * loud
+    assert (got["bars"][0, 2:] == 0.0).all()               # a pair of silent frames is exactly zero
+    assert (got["bars_i32"][0, 0] == 0).all() and (got["bars_i32"][0, 2:] == 0).all()
 
 
 @pytest.mark.parametrize("n", [512, 2048, 4096, 16384])

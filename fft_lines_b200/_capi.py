@@ -14,7 +14,7 @@ WINDOW_RECT, WINDOW_HANN = 0, 1
 BINNING_LINEAR, BINNING_LOG = 0, 1
 BEAT_SAMPLES, TEMPO_RING = 160, 256
 MOVE_EXACT, MOVE_REFERENCE = 0, 1
-KERNEL_AUTO, KERNEL_GENERIC = 0, 1
+KERNEL_AUTO, KERNEL_GENERIC, KERNEL_FAST_REGISTERS = 0, 1, 2
 
 
 class FftlConfig(C.Structure):
@@ -55,7 +55,7 @@ EXPORTED_FUNCTIONS = {
         "fftl_config_reference", "fftl_config_extended", "fftl_config_validate", "fftl_build_bins",
         "fftl_build_sg", "fftl_stft_create", "fftl_stft_destroy", "fftl_stft_num_frames", "fftl_stft_first_frame_needed",
         "fftl_stft_sample_span", "fftl_stft_run_device", "fftl_stft_run_device_span", "fftl_stft_run", "fftl_stft_launch_count",
-        "fftl_stft_fast_launch_count", "fftl_stft_set_kernel", "fftl_stft_timing",
+        "fftl_stft_fast_launch_count", "fftl_stft_tmem_launch_count", "fftl_stft_set_kernel", "fftl_stft_timing",
         "fftl_stream_create", "fftl_stream_destroy", "fftl_stream_reset", "fftl_stream_push_device",
         "fftl_stream_push", "fftl_stream_push_device_f32", "fftl_stream_launch_count", "fftl_stream_set_history", "fftl_stream_history_device",
         "fftl_stream_waveform_device", "fftl_settings_default", "fftl_settings_parse", "fftl_settings_format",
@@ -112,6 +112,8 @@ def lib():
                                             C.c_int64, vp, vp, vp, vp]
     L.fftl_stft_fast_launch_count.argtypes = [vp]
     L.fftl_stft_fast_launch_count.restype = C.c_int64
+    L.fftl_stft_tmem_launch_count.argtypes = [vp]
+    L.fftl_stft_tmem_launch_count.restype = C.c_int64
     L.fftl_stft_set_kernel.argtypes = [vp, C.c_int32]
     L.fftl_stft_run.argtypes = [vp, vp, C.c_int32, C.c_int64, C.c_int64, C.c_int64, C.c_int64, C.c_int64, vp, vp, vp]
     L.fftl_stft_launch_count.argtypes = [vp]

@@ -282,6 +282,7 @@ struct fftl_stft {
     int mag_bins;                   // highest bin any bar (or the bass bin) reads, + 1
     int num_sms;
     int64_t fast_launches;
+    int64_t tmem_launches;          // fast-path launches that took the tensor-memory variant (stft_rdif_tm.cuh)
     int kernel_select;              // FFTL_KERNEL_AUTO / FFTL_KERNEL_GENERIC (fftl_stft_set_kernel)
     int* d_aux;                     // [2][channels][nf_aux] (w then bass)
     size_t aux_capacity;            // ints
@@ -500,16 +501,17 @@ extern "C" int64_t fftl_stft_first_frame_needed(int64_t frame_begin, int32_t wit
 
 extern "C" int64_t fftl_stft_launch_count(const fftl_stft* h) { return h ? h->launches : 0; }
 extern "C" int64_t fftl_stft_fast_launch_count(const fftl_stft* h) { return h ? h->fast_launches : 0; }
+extern "C" int64_t fftl_stft_tmem_launch_count(const fftl_stft* h) { return h ? h->tmem_launches : 0; }
 
 extern "C" int fftl_stft_set_kernel(fftl_stft* h, int32_t which)
 {
     if (!h) return set_error(FFTL_ERR_ARG, "handle is NULL");
-    if (which != FFTL_KERNEL_AUTO && which != FFTL_KERNEL_GENERIC) return set_error(FFTL_ERR_ARG, "unknown kernel selection %d", which);
+    if (which != FFTL_KERNEL_AUTO && which != FFTL_KERNEL_GENERIC && which != FFTL_KERNEL_FAST_REGISTERS) return set_error(FFTL_ERR_ARG, "unknown kernel selection %d", which);
     h->kernel_select = which;
     return FFTL_OK;
 }
 
-static cudaError_t try_rdif(const fftl_stft* h, const StftParams& q, int channels, long long samples, cudaStream_t st)
+static cudaError_t try_rdif(const fftl_stft* h, const StftParams& q, int channels, long long samples, cudaStream_t st, int* used_tm)
 {
     const fftl_config& c = h->cfg;
     if (c.n != 16384 && c.n != 8192 && c.n != 4096 && c.n != 2048 && c.n != 1024) return cudaErrorNotSupported;
@@ -550,6 +552,7 @@ static cudaError_t try_rdif(const fftl_stft* h, const StftParams& q, int channel
     p.strict = q.strict;
     p.bass_bin = q.bass_bin;
     const int full_rows = c.n / 512;
+    p.mag_bins = h->mag_bins;
     p.mag_rows = (h->mag_bins + 255) / 256;       // bins < 256*rows are kept; all rows also keep bin N/2
     if (p.mag_rows > full_rows || h->mag_bins > c.n / 2) p.mag_rows = full_rows;
     if (c.n >= 8192) p.mag_rows = full_rows; // built with all rows only
@@ -557,6 +560,8 @@ static cudaError_t try_rdif(const fftl_stft* h, const StftParams& q, int channel
     for (int i = 0; i < 4; i++) p.beat_bars[i] = q.beat_bars[i];
     p.zoom = q.zoom;
     p.circle_add = q.circle_add;
+    p.no_tm = h->kernel_select == FFTL_KERNEL_FAST_REGISTERS;
+    p.used_tm = used_tm;
     const bool win = q.window != nullptr;
     switch (hopq) {
     case 0: return launch_rdif_h0(c.n, win, h->num_sms, p, channels, st);
@@ -607,12 +612,14 @@ static int run_range(fftl_stft* h, const int16_t* pcm, int channels, int64_t cst
     p.circle_add = c.circle ? 10.0f : 0.0f; // fft_lines.c:204-207
     long long pairs = (fe - compute_from + 1) / 2;
     if (evs) CUDA_TRY(cudaEventRecord(evs[0], st));
-    cudaError_t fe_ = force_generic ? cudaErrorNotSupported : try_rdif(h, p, channels, samples, st);
+    int used_tm = 0;
+    cudaError_t fe_ = force_generic ? cudaErrorNotSupported : try_rdif(h, p, channels, samples, st, &used_tm);
     if (fe_ == cudaErrorNotSupported) {
         CUDA_TRY(dispatch_stft(c.n, p, channels, pairs, st)); // generic kernel: any n, strided PCM, any hop
     } else {
         CUDA_TRY(fe_);
         h->fast_launches++;
+        h->tmem_launches += used_tm;
     }
     h->launches++;
     if (evs) CUDA_TRY(cudaEventRecord(evs[1], st));

@@ -21,18 +21,20 @@ static cudaError_t launch_rdif(int num_sms, RdifParams p, int channels, cudaStre
     constexpr bool RESIDENT = N != 16384; // two columns per thread at N = 16384: per-column constants are reloaded
     using Sh = RdifShape<N, F>;
 #ifndef FFTL_NO_TM
-    // N = 4096 with shared samples: three CTAs per SM with the per-thread constants in tensor memory (stft_rdif_tm.cuh)
-    if constexpr (N == 4096 && F == 4 && HOPQ > 0 && ROWS < 8) {
-        if (RdifTmShape::fits(p.bars_n, p.nseg, p.sg_half, ROWS)) {
+    // N = 4096 / 2048 with shared samples: more CTAs per SM with the per-thread constants in tensor memory (stft_rdif_tm.cuh)
+    if constexpr ((N == 4096 || N == 2048) && F == 4 && HOPQ > 0 && 256 * ROWS <= N / 2) {
+        using Ts = RdifTmShape<N>;
+        if (!p.no_tm && Ts::fits(p.bars_n, p.nseg, p.sg_half, ROWS, p.mag_bins)) {
             if (!rdif_set_tiles(p, channels, F, HOPQ, N)) return cudaErrorNotSupported;
             if (p.total_tiles <= 0) return cudaSuccess;
-            const size_t smem_tm = RdifTmShape::smem_bytes(p.bars_n, p.nseg, p.sg_half);
-            auto kern_tm = stft_bars_rdif_tm_kernel<HOPQ, WIN, SGW, ROWS>;
+            const size_t smem_tm = Ts::smem_bytes(p.bars_n, p.nseg, p.sg_half);
+            auto kern_tm = stft_bars_rdif_tm_kernel<N, HOPQ, WIN, SGW, ROWS>;
             cudaError_t e = cudaFuncSetAttribute(kern_tm, cudaFuncAttributeMaxDynamicSharedMemorySize, (int)smem_tm);
             if (e != cudaSuccess) return e;
-            long long grid = (long long)RdifTmShape::MINB * num_sms;
+            long long grid = (long long)Ts::MINB * num_sms;
             if (grid > p.total_tiles) grid = p.total_tiles;
-            kern_tm<<<(unsigned)grid, RdifTmShape::THREADS, smem_tm, st>>>(p);
+            if (p.used_tm) *p.used_tm = 1;
+            kern_tm<<<(unsigned)grid, Ts::THREADS, smem_tm, st>>>(p);
             return cudaGetLastError();
         }
     }
@@ -65,6 +67,7 @@ template <int HOPQ, bool WIN>
 static cudaError_t launch_rdif_2k(int num_sms, const RdifParams& p, int channels, cudaStream_t st)
 {
     if (p.mag_rows <= 1) return launch_rdif<2048, 4, HOPQ, WIN, -1, 1>(num_sms, p, channels, st);
+    if (HOPQ > 0 && p.sg_half == 3) return launch_rdif<2048, 4, HOPQ, WIN, 3, 4>(num_sms, p, channels, st); // the default smoothing width, unrolled
     return launch_rdif<2048, 4, HOPQ, WIN, -1, 4>(num_sms, p, channels, st);
 }
 

@@ -49,9 +49,12 @@ struct RdifParams {
     int* aux_bass;
     int hop, bars_n, nseg, sg_half, strict, bass_bin;
     int mag_rows;               // 256-bin rows of magnitudes that are kept (bins < 256*mag_rows, + bin N/2 when 8)
+    int mag_bins;               // bins < mag_bins are read by a bar or as the bass bin
     int mag_stride;             // float2 per frame pair in the magnitude area
     int beat_bars[4];
     float zoom, circle_add;
+    int no_tm;                  // host side only: keep the constants in registers (skip stft_rdif_tm.cuh)
+    int* used_tm;               // host side only: set to 1 by the launcher when the tensor-memory variant was launched
 };
 
 // Real 16-point DFT: x[0..15] real -> Y[0..8] (Y[0], Y[8] real).  66 flops.

@@ -135,8 +135,14 @@ class BatchedSpectrum:
         """How many of the bars-kernel launches took the real-input fast path."""
         return int(_capi.lib().fftl_stft_fast_launch_count(self._h))
 
+    @property
+    def tmem_launch_count(self):
+        """How many fast-path launches ran the tensor-memory variant (constants parked in TMEM, three CTAs per SM)."""
+        return int(_capi.lib().fftl_stft_tmem_launch_count(self._h))
+
     def set_kernel(self, which):
-        """_capi.KERNEL_AUTO (default) or _capi.KERNEL_GENERIC (the packed-complex baseline kernel)."""
+        """_capi.KERNEL_AUTO (default), _capi.KERNEL_GENERIC (the packed-complex baseline kernel) or
+        _capi.KERNEL_FAST_REGISTERS (the fast path without its tensor-memory variant)."""
         _capi.check(_capi.lib().fftl_stft_set_kernel(self._h, which))
 
     def sample_span(self, total_samples, frame_begin, frame_end, with_beat=True):

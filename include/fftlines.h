@@ -161,10 +161,14 @@ int fftl_stft_run(fftl_stft* h, const int16_t* pcm_host, int32_t channels,
 /* Number of kernel launches issued by this handle since creation; how many of them were the fast path. */
 int64_t fftl_stft_launch_count(const fftl_stft* h);
 int64_t fftl_stft_fast_launch_count(const fftl_stft* h);
+/* ... and how many of those ran the variant that parks its per-thread constants in tensor memory (n = 4096, hop 256 /
+ * 512 / 1024, fewer than 2048 bins read: three CTAs per SM instead of two). */
+int64_t fftl_stft_tmem_launch_count(const fftl_stft* h);
 /* Which bars kernel a handle uses: AUTO = the real-input fast path wherever it is built (n = 1024..16384), else the
  * generic packed-complex kernel; GENERIC = always the latter (the correctness baseline the fast path is tested
- * against).  Both are this library's own sm_100a kernels. */
-enum { FFTL_KERNEL_AUTO = 0, FFTL_KERNEL_GENERIC = 1 };
+ * against); FAST_REGISTERS = the fast path with its constants in registers even where the tensor-memory variant
+ * exists (the two give the same bits; tests compare them).  All are this library's own sm_100a kernels. */
+enum { FFTL_KERNEL_AUTO = 0, FFTL_KERNEL_GENERIC = 1, FFTL_KERNEL_FAST_REGISTERS = 2 };
 int fftl_stft_set_kernel(fftl_stft* h, int32_t which);
 /* Device time (ms, CUDA events recorded on the launching stream) summed over
  * the fftl_stft_run_device calls made since the previous fftl_stft_timing call

@@ -266,3 +266,36 @@ def test_fast_path_many_channels_few_frames(oracle, lib, n, hop):
     pcm = oracle.synth_pcm(channels, n + 8 * hop + 11)
     _check(oracle, lib, lib.extended_config(n, hop, 100), pcm)
     _check(oracle, lib, lib.reference_config(n, hop, 100), pcm, 3, 8)
+
+
+@pytest.mark.parametrize("n,hop,bars", [(4096, 256, 200), (4096, 512, 200), (4096, 1024, 200), (2048, 512, 100), (4096, 512, 64)])
+def test_tensor_memory_variant_equals_register_variant(oracle, lib, n, hop, bars):
+    """n = 4096 (hop 256 / 512 / 1024) and n = 2048 (hop 512) take the variant of the fast path that parks its per-thread
+    constants in tensor memory and writes the heights one tile late (stft_rdif_tm.cuh): the same arithmetic in the same
+    order as the register-resident kernel, so bars, (int) heights and beat records are equal bit for bit -- for a full
+    run, for a shard that starts and ends inside tiles, for a job shorter than one tile per CTA and for many short
+    channels."""
+    cfg = lib.extended_config(n, hop, bars)
+    for channels, frames in ((2, 1237), (1, 3), (37, 21)):
+        pcm = oracle.synth_pcm(channels, n + (frames - 1) * hop + 5)
+        with lib.BatchedSpectrum(cfg) as sp:
+            tm = sp.run(pcm)
+            assert sp.tmem_launch_count > 0
+            n_tm = sp.tmem_launch_count
+            part = sp.run(pcm, 1, frames - 1) if frames > 2 else None
+            sp.set_kernel(_capi.KERNEL_FAST_REGISTERS)
+            reg = sp.run(pcm)
+            assert sp.tmem_launch_count == (n_tm + (1 if part is not None else 0)) and sp.fast_launch_count > sp.tmem_launch_count
+        assert (tm["bars"] == reg["bars"]).all() and (tm["bars_i32"] == reg["bars_i32"]).all()
+        for k in BEAT_FIELDS:
+            assert (tm["beat"][k] == reg["beat"][k]).all(), k
+        if part is not None:
+            assert (part["bars"] == reg["bars"][:, 1:frames - 1]).all()
+            for k in BEAT_FIELDS:
+                assert (part["beat"][k] == reg["beat"][k][:, 1:frames - 1]).all(), k
+    # no room for the overlay when the whole band is read (n = 4096: bars up to the Nyquist frequency; n = 2048: one bar
+    # per bin including bin n/2): the register variant of the fast path runs
+    full = lib.extended_config(n, hop, bars, fmax=24000.0) if n == 4096 else lib.reference_config(n, hop, n // 2 + 1, zoom=1e-3)
+    with lib.BatchedSpectrum(full) as sp:
+        sp.run(oracle.synth_pcm(1, n + 9 * hop))
+        assert sp.fast_launch_count > 0 and sp.tmem_launch_count == 0

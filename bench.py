@@ -501,6 +501,8 @@ def main():
     clocks = sampler.stop()
     ms_total = max_over_ranks(e0.elapsed_time(e1))
     launches = sp.launch_count - l0
+    bars_kernel_name = ("stft_bars_rdif_tm_kernel<4096> (fast path, per-thread constants in tensor memory; csrc/stft_rdif_tm.cuh)" if sp.tmem_launch_count > 0 else
+                        "stft_bars_rdif_kernel<4096> (fast path, register-resident constants)" if sp.fast_launch_count > 0 else "stft_bars_kernel<4096> (generic)")
     calls, tot_ms, bars_ms = sp.timing()
     bars_kernel_ms = max_over_ranks(bars_ms / max(calls, 1))
     value = world * frames_per_step * args.steps / (ms_total * 1e-3)
@@ -599,7 +601,7 @@ def main():
                 traffic_note = "stale: %s was captured from other kernel sources (hash %s, now %s)" % (
                     tj.get("source"), tj.get("kernel_source_hash"), kernel_source_hash())
         roof = {
-            "bound": "fp32", "kernel": "stft_bars_rdif_kernel<4096> (fast path; generic fallback: stft_bars_kernel<N>)",
+            "bound": "fp32", "kernel": bars_kernel_name,
             "achieved": achieved_tf, "peak": fp32_peak, "unit": "TFLOP/s", "frac": achieved_tf / fp32_peak,
             "peak_source": "FP32 FMA probe run in this process (not in MEASURED_PEAKS.json); nominal %.2f" % NOMINAL_FP32_TFLOPS,
             "frac_of_nominal": achieved_tf / NOMINAL_FP32_TFLOPS,

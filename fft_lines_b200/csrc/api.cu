@@ -922,6 +922,7 @@ struct fftl_stream {
     int* d_w_ring;          // [streams][160]
     int* d_w_sum;           // [streams]
     int* d_tempo_ring;      // [streams][256]
+    double2* d_tempo_x;     // [streams][129] transform of the tempo ring, carried from tick to tick (stream_beat_carry_kernel)
     StreamState* d_state;
     // staging for the host-buffer variant
     int16_t* d_fresh;
@@ -947,6 +948,7 @@ extern "C" void fftl_stream_destroy(fftl_stream* s)
     cudaFree(s->d_w_ring);
     cudaFree(s->d_w_sum);
     cudaFree(s->d_tempo_ring);
+    cudaFree(s->d_tempo_x);
     cudaFree(s->d_state);
     cudaFree(s->d_fresh);
     cudaFree(s->d_conv);
@@ -969,6 +971,7 @@ extern "C" int fftl_stream_reset(fftl_stream* s)
     CUDA_TRY(cudaMemset(s->d_w_ring, 0, sizeof(int) * S * FFTL_BEAT_SAMPLES));
     CUDA_TRY(cudaMemset(s->d_w_sum, 0, sizeof(int) * S));
     CUDA_TRY(cudaMemset(s->d_tempo_ring, 0, sizeof(int) * S * FFTL_TEMPO_RING));
+    CUDA_TRY(cudaMemset(s->d_tempo_x, 0, sizeof(double2) * S * STREAM_CARRY_BINS)); // the exact transform of the zero ring
     CUDA_TRY(cudaMemset(s->d_state, 0, sizeof(StreamState)));
     if (s->d_hist) CUDA_TRY(cudaMemset(s->d_hist, 0, sizeof(float) * S * s->hist_depth * s->core->cfg.bars));
     // the memsets run on the legacy stream, pushes on non-blocking / caller streams: finish them before returning
@@ -1048,6 +1051,7 @@ extern "C" int fftl_stream_create(const fftl_config* cfg, int32_t streams, int32
     if (e == cudaSuccess) e = cudaMalloc(&s->d_w_ring, sizeof(int) * S * FFTL_BEAT_SAMPLES);
     if (e == cudaSuccess) e = cudaMalloc(&s->d_w_sum, sizeof(int) * S);
     if (e == cudaSuccess) e = cudaMalloc(&s->d_tempo_ring, sizeof(int) * S * FFTL_TEMPO_RING);
+    if (e == cudaSuccess) e = cudaMalloc(&s->d_tempo_x, sizeof(double2) * S * STREAM_CARRY_BINS);
     if (e == cudaSuccess) e = cudaMalloc(&s->d_state, sizeof(StreamState));
     if (e == cudaSuccess) e = cudaMalloc(&s->d_bars, sizeof(float) * S * B);
     if (e == cudaSuccess) e = cudaMalloc(&s->d_bars_i32, sizeof(int32_t) * S * B);
@@ -1118,7 +1122,16 @@ extern "C" int fftl_stream_push_device(fftl_stream* s, const int16_t* fresh, int
     bp.n_times_dt = (float)c.n * dt;
     bp.strict = c.strict_int;
     bp.finish = s->d_hist ? 0 : 1; // the history push, when enabled, is the last kernel
-    stream_beat_kernel<<<(s->streams + 31) / 32, 256, 0, st>>>(bp);
+    if (h->d_tw256d) {
+        // the tempo ring's transform is carried from tick to tick: no 256-point FFT in the tick's critical path
+        StreamCarryParams cp;
+        cp.b = bp;
+        cp.x = s->d_tempo_x;
+        cp.tw256d = h->d_tw256d;
+        stream_beat_carry_kernel<<<(s->streams + 1) / 2, 256, 0, st>>>(cp);
+    } else {
+        stream_beat_kernel<<<(s->streams + 31) / 32, 256, 0, st>>>(bp);
+    }
     CUDA_TRY(cudaGetLastError());
     if (s->d_hist) {
         long long total = (long long)s->streams * c.bars;

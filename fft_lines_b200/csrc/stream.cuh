@@ -256,6 +256,131 @@ __global__ void __launch_bounds__(256) stream_beat_kernel(const StreamBeatParams
     if (p.finish) stream_finish(p.state);
 }
 
+// The same stage with the tempo ring's 256-point transform CARRIED from tick to tick instead of recomputed
+// (the streaming form of beat_post_kernel's update, kernels.cuh): a tick changes one slot of the ring
+// (beatDetector.c:53-59), so
+//     X[k] += (ring_new - ring_old) * W256^(pos k),   k = 0..128 (the ring is real: bins 129..160 mirror 127..96)
+// in double with double twiddles (1e-16 per tick, no drift that matters in any run length; a reset zeroes X with the
+// ring, which is its exact transform).  No FFT, no shuffles: one thread per bin, two streams per CTA of 256 threads,
+// |X|^2 in double -> float -> correctly rounded square root -> (int) as in beat_ring_steps.  The dependent chain of a
+// tick is tick -> old ring value -> fma -> sqrt -> scan instead of 16 ring loads -> 256-point transform -> untangle.
+struct StreamCarryParams {
+    StreamBeatParams b;
+    double2* x;             // [streams][129] carried transform
+    const double2* tw256d;  // W256^m in double
+};
+
+constexpr int STREAM_CARRY_BINS = FFTL_TEMPO_RING / 2 + 1; // 129
+
+__global__ void __launch_bounds__(256) stream_beat_carry_kernel(const StreamCarryParams q)
+{
+    const StreamBeatParams& p = q.b;
+    __shared__ int s_h[2][FFTL_BEAT_SAMPLES + 4]; // heightBuffer[0..160] of the CTA's two streams
+    const int tid = threadIdx.x;
+    const int half = tid >> 7, k = tid & 127;
+    const int s = blockIdx.x * 2 + half;
+    const bool valid = s < p.streams;
+    const long long tick = p.state->tick;
+    const int pos256 = (int)(tick % FFTL_TEMPO_RING), pos160 = (int)(tick % FFTL_BEAT_SAMPLES);
+    int* ring = p.tempo_ring + (long long)s * FFTL_TEMPO_RING;
+    int nv = 0;
+    if (valid) {
+        // the reference transforms the ring as floats (beatDetector.c:61-65)
+        nv = p.aux_bass[s];
+        const double delta = (double)(float)nv - (double)(float)ring[pos256];
+        double2* xs = q.x + (long long)s * STREAM_CARRY_BINS;
+        auto bin = [&](const int kk) {
+            const double2 w = __ldg(q.tw256d + ((pos256 * kk) & (FFTL_TEMPO_RING - 1)));
+            double2 x = xs[kk];
+            x.x = fma(delta, w.x, x.x);
+            x.y = fma(delta, w.y, x.y);
+            xs[kk] = x;
+            const float mag = __fsqrt_rn(f64_to_f32(fma(x.x, x.x, x.y * x.y))); // correctly rounded: feeds an (int) cast
+            const int hv = trunc_i32(mag, p.strict);
+            s_h[half][kk] = hv;
+            if (kk >= 96 && kk < 128) s_h[half][FFTL_TEMPO_RING - kk] = hv; // |X[256-k]| = |X[k]|: bins 129..160
+        };
+        bin(k);
+        if (k == 0) bin(128);
+    }
+    __syncthreads();
+    if (valid && k == 0) ring[pos256] = nv; // every thread of the stream has read the old value
+    if (tid < 16) {
+        // peak scan, 8 lanes per stream (same code shape as beat_post_kernel)
+        const int si = tid >> 3, sub = tid & 7;
+        const int ss = blockIdx.x * 2 + si;
+        const int* h = s_h[si];
+        const int i0 = 20 * sub;
+        unsigned bits = 0;
+        int prev = (i0 == 0) ? 0 : h[i0 - 1];
+        int cur = h[i0];
+#pragma unroll
+        for (int qq = 0; qq < 20; qq++) {
+            int nxt = h[i0 + qq + 1];
+            int dold = (i0 + qq == 0) ? 0 : wrap_sub(cur, prev);
+            int dnew = wrap_sub(nxt, cur);
+            if (dold >= 0 && dnew <= 0) bits |= 1u << qq;
+            prev = cur;
+            cur = nxt;
+        }
+        int cnt = __popc(bits), incl = cnt;
+#pragma unroll
+        for (int o = 1; o < 8; o <<= 1) {
+            int n = __shfl_up_sync(0xffffu, incl, o, 8);
+            if (sub >= o) incl += n;
+        }
+        int rank = incl - cnt;
+        int best_val = 0, best_idx = -1;
+        int first = bits ? (i0 + __ffs(bits) - 1) : 1 << 30;
+        unsigned bb = bits;
+        while (bb) {
+            int qq = __ffs(bb) - 1;
+            bb &= bb - 1;
+            int i = i0 + qq;
+            int hv = h[i];
+            if (rank < 30 && i > 30 && hv > best_val) {
+                best_val = hv;
+                best_idx = i;
+            }
+            rank++;
+        }
+#pragma unroll
+        for (int o = 4; o > 0; o >>= 1) {
+            int ov = __shfl_xor_sync(0xffffu, best_val, o, 8);
+            int oi = __shfl_xor_sync(0xffffu, best_idx, o, 8);
+            int of = __shfl_xor_sync(0xffffu, first, o, 8);
+            bool take = (oi >= 0) && (best_idx < 0 || ov > best_val || (ov == best_val && oi < best_idx));
+            if (take) {
+                best_val = ov;
+                best_idx = oi;
+            }
+            first = of < first ? of : first;
+        }
+        if (sub == 0 && ss < p.streams) {
+            const int peak = best_idx >= 0 ? best_idx : (first < (1 << 30) ? first : 0);
+            // AddBeatSample (beatDetector.c:30-44) on the stream's own ring
+            const int w = p.aux_w[ss];
+            int* wr = p.w_ring + (long long)ss * FFTL_BEAT_SAMPLES;
+            int sum = wrap_sub(wrap_add(p.w_sum[ss], w), wr[pos160]);
+            wr[pos160] = w;
+            p.w_sum[ss] = sum;
+            const int thr = sum / FFTL_BEAT_SAMPLES;
+            const float qv = __fdiv_rn((float)w, (float)thr);
+            fftl_beat rec;
+            rec.w = w;
+            rec.thr = thr;
+            rec.beat_value = trunc_i32(__fmul_rn(qv, 128.0f), 1);
+            rec.flag = (thr > 0 && w > thr) ? 1 : 0;
+            rec.bass = p.aux_bass[ss];
+            rec.peak_index = peak;
+            rec.movement_per_sec = __fmul_rn(p.n_times_dt, (float)peak);
+            rec.reserved = 0;
+            p.out[ss] = rec;
+        }
+    }
+    if (p.finish) stream_finish(p.state);
+}
+
 // history ring: hist[s][tick % depth][b] = bars[s][b]
 __global__ void __launch_bounds__(256) stream_history_push_kernel(float* __restrict__ hist, const float* __restrict__ bars,
                                                                   StreamState* state, int streams, int depth, int nbars)

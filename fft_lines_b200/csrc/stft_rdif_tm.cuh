@@ -199,7 +199,8 @@ __global__ void __launch_bounds__(RdifTmShape<N>::THREADS, RdifTmShape<N>::MINB)
     asm volatile("tcgen05.fence::after_thread_sync;" ::: "memory");
     const uint32_t tm_base = *tm_holder;
     // this warp's 64 columns of its 32-lane quarter: [0, 16) window column, [16, 32) W_N^(t k0), [32, 64) W_M^(jj r)
-    const uint32_t tm = tm_base + ((uint32_t)(32 * (warp & 3)) << 16) + (uint32_t)(warp >> 2) * 64;
+    const int warp_u = __shfl_sync(0xffffffffu, warp, 0); // tells the compiler the value is warp-uniform: the TMEM address stays in a uniform register
+    const uint32_t tm = tm_base + ((uint32_t)(32 * (warp_u & 3)) << 16) + (uint32_t)(warp_u >> 2) * 64;
     {
         float c[32];
 #pragma unroll

@@ -275,8 +275,30 @@ def test_tensor_memory_variant_equals_register_variant(oracle, lib, n, hop, bars
     order as the register-resident kernel, so bars, (int) heights and beat records are equal bit for bit -- for a full
     run, for a shard that starts and ends inside tiles, for a job shorter than one tile per CTA and for many short
     channels."""
-    cfg = lib.extended_config(n, hop, bars)
-    for channels, frames in ((2, 1237), (1, 3), (37, 21)):
+    _tm_equals_registers(oracle, lib, lib.extended_config(n, hop, bars), n, hop)
+    # no room for the overlay when the whole band is read (n = 4096: bars up to the Nyquist frequency; n = 2048: one bar
+    # per bin including bin n/2): the register variant of the fast path runs
+    full = lib.extended_config(n, hop, bars, fmax=24000.0) if n == 4096 else lib.reference_config(n, hop, n // 2 + 1, zoom=1e-3)
+    with lib.BatchedSpectrum(full) as sp:
+        sp.run(oracle.synth_pcm(1, n + 9 * hop))
+        assert sp.fast_launch_count > 0 and sp.tmem_launch_count == 0
+
+
+@pytest.mark.parametrize("which", ["parity_rows1", "sg_off", "sg_runtime_width", "rows4", "circle"])
+def test_tensor_memory_variant_other_instantiations(oracle, lib, which):
+    """The other template instantiations of the tensor-memory kernel at n = 4096, hop 512: one magnitude row without a
+    window (the reference's chain), Savitzky-Golay off / at a run-time width, four magnitude rows, circle mode."""
+    n, hop = 4096, 512
+    cfg = {"parity_rows1": lambda: lib.reference_config(n, hop, 100, zoom=1e-3),
+           "sg_off": lambda: lib.extended_config(n, hop, 200, sg_half=0),
+           "sg_runtime_width": lambda: lib.extended_config(n, hop, 200, sg_half=5, sg_degree=3),
+           "rows4": lambda: lib.extended_config(n, hop, 150, fmax=11000.0),
+           "circle": lambda: lib.extended_config(n, hop, 200, circle=1)}[which]()
+    _tm_equals_registers(oracle, lib, cfg, n, hop, shapes=((2, 517), (3, 5)))
+
+
+def _tm_equals_registers(oracle, lib, cfg, n, hop, shapes=((2, 1237), (1, 3), (37, 21))):
+    for channels, frames in shapes:
         pcm = oracle.synth_pcm(channels, n + (frames - 1) * hop + 5)
         with lib.BatchedSpectrum(cfg) as sp:
             tm = sp.run(pcm)
@@ -291,11 +313,6 @@ def test_tensor_memory_variant_equals_register_variant(oracle, lib, n, hop, bars
             assert (tm["beat"][k] == reg["beat"][k]).all(), k
         if part is not None:
             assert (part["bars"] == reg["bars"][:, 1:frames - 1]).all()
+            assert (part["bars_i32"] == reg["bars_i32"][:, 1:frames - 1]).all()
             for k in BEAT_FIELDS:
                 assert (part["beat"][k] == reg["beat"][k][:, 1:frames - 1]).all(), k
-    # no room for the overlay when the whole band is read (n = 4096: bars up to the Nyquist frequency; n = 2048: one bar
-    # per bin including bin n/2): the register variant of the fast path runs
-    full = lib.extended_config(n, hop, bars, fmax=24000.0) if n == 4096 else lib.reference_config(n, hop, n // 2 + 1, zoom=1e-3)
-    with lib.BatchedSpectrum(full) as sp:
-        sp.run(oracle.synth_pcm(1, n + 9 * hop))
-        assert sp.fast_launch_count > 0 and sp.tmem_launch_count == 0

@@ -316,3 +316,36 @@ def _tm_equals_registers(oracle, lib, cfg, n, hop, shapes=((2, 1237), (1, 3), (3
             assert (part["bars_i32"] == reg["bars_i32"][:, 1:frames - 1]).all()
             for k in BEAT_FIELDS:
                 assert (part["beat"][k] == reg["beat"][k][:, 1:frames - 1]).all(), k
+
+
+def test_tensor_memory_variant_is_race_free_under_repetition(oracle, lib):
+    """The tensor-memory kernel hands buffers between phases with one split barrier and four CTA barriers per tile
+    (stft_rdif_tm.cuh): a missing one shows up as run-to-run differences (that is how the barrier in front of the next
+    tile's pass A was found missing during development).  Forty device-resident runs of a job with ~25 tiles per CTA,
+    with a second stream keeping the memory system busy, must all equal the register variant bit for bit."""
+    import torch
+    cfg = lib.extended_config(4096, 512, 200)
+    frames = 22000
+    d = torch.empty((2, 4096 + (frames - 1) * 512), dtype=torch.int16, device="cuda")
+    lib.synth_pcm_device(d)
+    noise_a = torch.empty(64 << 20, dtype=torch.uint8, device="cuda")
+    noise_b = torch.empty_like(noise_a)
+    side = torch.cuda.Stream()
+    with lib.BatchedSpectrum(cfg) as sp:
+        bars, _, beat = sp.alloc_device_outputs(2, frames, "cuda", want_i32=False)
+        sp.set_kernel(_capi.KERNEL_FAST_REGISTERS)
+        sp.run_device(d, bars, None, beat)
+        torch.cuda.synchronize()
+        ref_bars, ref_beat = bars.clone(), beat.clone()
+        sp.set_kernel(_capi.KERNEL_AUTO)
+        for it in range(40):
+            bars.zero_()
+            beat.zero_()
+            if it % 2:
+                with torch.cuda.stream(side):
+                    noise_b.copy_(noise_a, non_blocking=True)
+            sp.run_device(d, bars, None, beat)
+            torch.cuda.synchronize()
+            assert torch.equal(bars, ref_bars), "run %d" % it
+            assert torch.equal(beat, ref_beat), "run %d" % it
+        assert sp.tmem_launch_count == 40

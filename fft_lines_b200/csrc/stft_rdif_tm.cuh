@@ -1,4 +1,5 @@
-// stft_rdif_tm.cuh -- the N = 4096 / 2048 fast path with its per-thread constants parked in tensor memory (sm_100a).
+// stft_rdif_tm.cuh -- the N = 4096 / 2048 fast path with its per-thread constants parked in tensor memory (sm_100a):
+// N = 4096 at any hop, planar or interleaved PCM; N = 2048 at hop 512.
 //
 // stft_bars_rdif_kernel<4096, ...> (stft_rdif.cuh) keeps 62 per-thread constants in registers for the whole
 // tile loop (window column, pass-A twiddles, pass-C twiddles): 127 registers, two CTAs of 256 threads per SM,
@@ -82,8 +83,8 @@ __device__ __forceinline__ void tmem_wait16(float* v)
 }
 
 // TileCursor (stft_rdif.cuh) without the two 64-bit per-advance steps held in registers: they are recomputed from the
-// launch parameters (constant bank) once per tile.  Planar PCM only (sample_stride 1).
-struct TileCursorLean {
+// launch parameters (constant bank) once per tile.  STRIDED: p.sample_stride may differ from 1 (interleaved PCM).
+template <bool STRIDED> struct TileCursorLeanT {
     int left, tic, ch;
     const int16_t* xp;
     long long o0;
@@ -93,19 +94,19 @@ struct TileCursorLean {
         ch = (int)(first / p.tiles_per_channel);
         tic = (int)(first - (long long)ch * p.tiles_per_channel);
         const long long f0 = p.frame0 + (long long)tic * F;
-        xp = p.pcm + (long long)ch * p.channel_stride + f0 * p.hop;
+        xp = p.pcm + (long long)ch * p.channel_stride + f0 * p.hop * (STRIDED ? p.sample_stride : 1);
         o0 = ((long long)ch * p.nf_emit + (f0 - p.frame_emit)) * p.bars_n;
     }
     __device__ __forceinline__ void advance(const RdifParams& p, int stride, int F)
     {
         left--;
         tic += stride;
-        xp += (long long)(stride * F) * p.hop;
+        xp += (long long)(stride * F) * p.hop * (STRIDED ? p.sample_stride : 1);
         o0 += (long long)(stride * F) * p.bars_n;
         while (tic >= (int)p.tiles_per_channel) {
             tic -= (int)p.tiles_per_channel;
             ch++;
-            xp += p.channel_stride - p.tiles_per_channel * F * p.hop;
+            xp += p.channel_stride - p.tiles_per_channel * F * p.hop * (STRIDED ? p.sample_stride : 1);
             o0 += (p.nf_emit - p.tiles_per_channel * F) * p.bars_n;
         }
     }
@@ -159,9 +160,12 @@ __global__ void __launch_bounds__(RdifTmShape<N>::THREADS, RdifTmShape<N>::MINB)
     using Ts = RdifTmShape<N>;
     constexpr int F = Ts::F, M = Ts::M, SLOT = Ts::SLOT, THREADS = Ts::THREADS, SUBG = Ts::SUBG;
     constexpr int MAGS = Ts::mags(ROWS);
-    static_assert(HOPQ == 1 || HOPQ == 2 || HOPQ == 4, "the tile's frames share their samples");
+    // HOPQ = 1, 2, 4: hop = HOPQ*M, the tile's frames share their samples (NX per column and tile);
+    // HOPQ = 0: any hop, planar or interleaved PCM: every frame loads its own 16 samples per column, the next frame's
+    // while the current one is transformed
+    static_assert(HOPQ == 0 || HOPQ == 1 || HOPQ == 2 || HOPQ == 4, "hop variants");
     static_assert(ROWS >= 1 && 256 * ROWS <= N / 2, "magnitude rows");
-    constexpr int NX = 16 + HOPQ * (F - 1);
+    constexpr int NX = HOPQ ? 16 + HOPQ * (F - 1) : 16;
     // second sub-pass: M = 256: one radix-16 butterfly per lane; M = 128: NT = 2 radix-8 butterflies per lane (jj = j + SUBG tt)
     constexpr int R2 = M == 256 ? 16 : 8, NT = 16 / R2, HALF = R2 / 2;
     constexpr int NMG = NT * 2 * (ROWS < HALF ? ROWS : HALF); // magnitudes a thread produces per sub-transform
@@ -227,7 +231,7 @@ __global__ void __launch_bounds__(RdifTmShape<N>::THREADS, RdifTmShape<N>::MINB)
         tmem_wait_st();
     }
 
-    TileCursorLean cur;
+    TileCursorLeanT<HOPQ == 0> cur;
     cur.init(p, blockIdx.x, gridDim.x, F);
     // Heights of a tile are written one tile late: the Savitzky-Golay + store step of tile i-1 runs in the middle of
     // pass B/C of tile i, on warps 1.. only -- warp 0 owns the two packed slots, whose untangling costs it ~70
@@ -244,15 +248,33 @@ __global__ void __launch_bounds__(RdifTmShape<N>::THREADS, RdifTmShape<N>::MINB)
     };
     for (; cur.left > 0;) {
         // ================= pass A (both frame pairs) =================
-        float xr[NX];
-        const int16_t* xp = cur.xp + t;
-        if (cur.tic < p.tic_full) { // every sample the tile reads exists
+        float xr[NX], xn[HOPQ ? 1 : 16]; // HOPQ = 0: the frame being transformed / the next one (roles swap per frame)
+        const bool all_samples = cur.tic < p.tic_full; // every sample the tile reads exists
+        // HOPQ = 0: the 16 samples of column t of frame f of the tile
+        auto load_frame = [&](const int f, float* x) {
+            const long long ss = p.sample_stride;
+            const int16_t* xf = cur.xp + (t + (long long)f * p.hop) * ss;
+            if (all_samples) {
 #pragma unroll
-            for (int r = 0; r < NX; r++) xr[r] = pcm_to_float(xp + r * M);
+                for (int q = 0; q < 16; q++) x[q] = pcm_to_float(xf + (long long)q * M * ss);
+            } else {
+                const long long s0 = (cur.first_frame(p, F) + f) * (long long)p.hop + t;
+#pragma unroll
+                for (int q = 0; q < 16; q++) x[q] = (s0 + (long long)q * M < p.samples) ? pcm_to_float(xf + (long long)q * M * ss) : 0.0f;
+            }
+        };
+        if constexpr (HOPQ == 0) {
+            load_frame(0, xr);
         } else {
-            const long long s0 = cur.first_frame(p, F) * (long long)p.hop; // the tile's first sample
+            const int16_t* xp = cur.xp + t;
+            if (all_samples) {
 #pragma unroll
-            for (int r = 0; r < NX; r++) xr[r] = (s0 + t + (long long)r * M < p.samples) ? pcm_to_float(xp + r * M) : 0.0f;
+                for (int r = 0; r < NX; r++) xr[r] = pcm_to_float(xp + r * M);
+            } else {
+                const long long s0 = cur.first_frame(p, F) * (long long)p.hop; // the tile's first sample
+#pragma unroll
+                for (int r = 0; r < NX; r++) xr[r] = (s0 + t + (long long)r * M < p.samples) ? pcm_to_float(xp + r * M) : 0.0f;
+            }
         }
         if (have_prev) { // every thread is done with the previous tile's magnitudes and segment sums
             mbar_wait(mb, mb_parity);
@@ -272,8 +294,21 @@ __global__ void __launch_bounds__(RdifTmShape<N>::THREADS, RdifTmShape<N>::MINB)
                 float cw[16], ct[16];
                 if (WINDOWED) tmem_ld16_async(tm, cw);
                 tmem_ld16_async(tm + 16, ct);
-                if (WINDOWED) tmem_wait16(cw);
-                real_dft16<WINDOWED>(xr + HOPQ * f, cw, yr, yi);
+                if constexpr (HOPQ == 0) {
+                    // frames alternate between the two sample buffers; the next frame's loads travel during this frame's twiddle
+                    // multiplies and slot stores and the other CTAs' work
+                    float* xc = (f & 1) ? xn : xr;
+                    float* xnext = (f & 1) ? xr : xn;
+                    if (WINDOWED) tmem_wait16(cw);
+                    float xcur[16];
+#pragma unroll
+                    for (int q = 0; q < 16; q++) xcur[q] = xc[q];
+                    real_dft16<WINDOWED>(xcur, cw, yr, yi);
+                    if (f + 1 < F) load_frame(f + 1, xnext); // behind the DFT: in front of it 14 registers spill (169 vs 175 M frames/s)
+                } else {
+                    if (WINDOWED) tmem_wait16(cw);
+                    real_dft16<WINDOWED>(xr + HOPQ * f, cw, yr, yi);
+                }
                 tmem_wait16(ct);
                 y0[h] = yr[0];
                 y8[h] = yr[8];

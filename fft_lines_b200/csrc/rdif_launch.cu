@@ -23,7 +23,7 @@ static cudaError_t launch_rdif(int num_sms, RdifParams p, int channels, cudaStre
 #ifndef FFTL_NO_TM
     // N = 4096 / 2048 with shared samples: more CTAs per SM with the per-thread constants in tensor memory (stft_rdif_tm.cuh)
     // (N = 2048 with one magnitude row, i.e. the reference's own 100-bar configuration, is 3 % faster from registers: measured)
-    if constexpr ((N == 4096 || (N == 2048 && ROWS > 1)) && F == 4 && (HOPQ > 0 || N == 4096) && 256 * ROWS <= N / 2) {
+    if constexpr ((N == 4096 || (N == 2048 && ROWS > 1)) && F == 4 && 256 * ROWS <= N / 2) {
         using Ts = RdifTmShape<N>;
         if (!p.no_tm && Ts::fits(p.bars_n, p.nseg, p.sg_half, ROWS, p.mag_bins)) {
             if (!rdif_set_tiles(p, channels, F, HOPQ, N)) return cudaErrorNotSupported;

@@ -1,5 +1,5 @@
 // stft_rdif_tm.cuh -- the N = 4096 / 2048 fast path with its per-thread constants parked in tensor memory (sm_100a):
-// N = 4096 at any hop, planar or interleaved PCM; N = 2048 at hop 512.
+// any hop, planar or interleaved PCM.
 //
 // stft_bars_rdif_kernel<4096, ...> (stft_rdif.cuh) keeps 62 per-thread constants in registers for the whole
 // tile loop (window column, pass-A twiddles, pass-C twiddles): 127 registers, two CTAs of 256 threads per SM,

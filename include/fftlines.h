@@ -161,8 +161,8 @@ int fftl_stft_run(fftl_stft* h, const int16_t* pcm_host, int32_t channels,
 /* Number of kernel launches issued by this handle since creation; how many of them were the fast path. */
 int64_t fftl_stft_launch_count(const fftl_stft* h);
 int64_t fftl_stft_fast_launch_count(const fftl_stft* h);
-/* ... and how many of those ran the variant that parks its per-thread constants in tensor memory (n = 4096 at any hop
- * with fewer than 2048 bins read: three CTAs per SM instead of two; n = 2048 at hop 512). */
+/* ... and how many of those ran the variant that parks its per-thread constants in tensor memory (n = 4096 with fewer
+ * than 2048 bins read: three CTAs per SM instead of two; n = 2048 with more than 256 and fewer than 1025). */
 int64_t fftl_stft_tmem_launch_count(const fftl_stft* h);
 /* Which bars kernel a handle uses: AUTO = the real-input fast path wherever it is built (n = 1024..16384), else the
  * generic packed-complex kernel; GENERIC = always the latter (the correctness baseline the fast path is tested

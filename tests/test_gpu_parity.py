@@ -269,7 +269,7 @@ def test_fast_path_many_channels_few_frames(oracle, lib, n, hop):
 
 
 @pytest.mark.parametrize("n,hop,bars", [(4096, 256, 200), (4096, 512, 200), (4096, 1024, 200), (2048, 512, 100), (4096, 512, 64), (4096, 480, 200),
-                                        (4096, 441, 200), (4096, 5000, 200)])
+                                        (4096, 441, 200), (4096, 5000, 200), (2048, 480, 100)])
 def test_tensor_memory_variant_equals_register_variant(oracle, lib, n, hop, bars):
     """n = 4096 (hop 256 / 512 / 1024) and n = 2048 (hop 512) take the variant of the fast path that parks its per-thread
     constants in tensor memory and writes the heights one tile late (stft_rdif_tm.cuh): the same arithmetic in the same

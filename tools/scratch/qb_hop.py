@@ -2,8 +2,9 @@
 import sys, time, torch
 sys.path.insert(0, ".")
 import fft_lines_b200 as F
-hop = int(sys.argv[1]); inter = len(sys.argv) > 2
-n, bars, ch = 4096, 200, 2
+hop = int(sys.argv[1]); inter = len(sys.argv) > 2 and sys.argv[2] == 'i'
+n = int(sys.argv[3]) if len(sys.argv) > 3 else 4096
+bars, ch = (200 if n == 4096 else 100), 2
 S = 48000 * 3600
 cfg = F.extended_config(n, hop, bars)
 pcm = torch.empty((ch, S), dtype=torch.int16, device="cuda")

@@ -150,3 +150,36 @@ def test_history_ring_and_waveform(oracle, lib):
         wf = ss.waveform_device(points=2048, scale=0.02, offset=float(off)).cpu().numpy()
         want = (win.astype(np.float32) * np.float32(0.02) + off).astype(np.int32)
         assert (wf == want).all()
+
+
+def test_streaming_tempo_transform_carried_across_ring_wraps(oracle, lib):
+    """The streaming beat stage carries the 256-point transform of the tempo ring from tick to tick
+    (stream_beat_carry_kernel): X[k] += (new - old) * W256^(pos k).  700 ticks wrap the 256-slot ring almost three times,
+    so old values are non-zero and subtracted; a reset in the middle must restart from the zero ring.  The integer
+    stages are replayed by the oracle on the GPU's own (w, bass) series (bit exact), every tempo index is equal to the
+    fp64 oracle's or an explained integer-boundary flip (helpers.assert_peaks_explained)."""
+    n, B, streams, count, ticks = 1024, 32, 5, 128, 700
+    cfg = lib.extended_config(n, count, B)
+    oc = oracle.Config()
+    import ctypes as C
+    C.memmove(C.byref(oc), C.byref(cfg), C.sizeof(oc))
+    rng = np.random.default_rng(5)
+    # loud, strongly varying material so that the bass bin (and with it the tempo ring) moves a lot
+    env = (1.0 + np.sin(np.arange(ticks * count) * 2 * np.pi / (count * 37.0))) * 0.5
+    src = (rng.normal(0, 9000, (streams, ticks * count)) * env + 6000 * np.sin(np.arange(ticks * count) * 2 * np.pi * 90.0 / 48000.0) * env)
+    src = src.clip(-32768, 32767).astype(np.int16)
+    recs = []
+    with lib.StreamingSpectrum(cfg, streams) as ss:
+        for k in range(ticks):
+            recs.append(ss.push(src[:, k * count:(k + 1) * count], want_i32=False)["beat"].copy())
+        n_dt = np.full(ticks, np.float32(n) * (np.float32(count) / np.float32(cfg.sample_rate)), np.float32)
+        for s in range(streams):
+            series = np.array([recs[k][s] for k in range(ticks)], dtype=recs[0].dtype)
+            assert len(set(series["bass"][300:].tolist())) > 50       # the ring really changes
+            assert_peaks_explained(oracle, oc, series, "stream %d" % s, n_dt=n_dt)
+        # after a reset the carried transform starts again from the zero ring: the same input gives the same records
+        ss.reset()
+        again = [ss.push(src[:, k * count:(k + 1) * count], want_i32=False)["beat"].copy() for k in range(300)]
+        for k in range(300):
+            for name in recs[0].dtype.names:
+                assert (again[k][name] == recs[k][name]).all(), (k, name)

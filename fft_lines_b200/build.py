@@ -18,7 +18,7 @@ UNITS = [("api.cu", [], "api"),
          ("rdif_launch.cu", ["-DFFTL_RDIF_HOPQ=0"], "rdif_h0"), ("rdif_launch.cu", ["-DFFTL_RDIF_HOPQ=1"], "rdif_h1"),
          ("rdif_launch.cu", ["-DFFTL_RDIF_HOPQ=2"], "rdif_h2"), ("rdif_launch.cu", ["-DFFTL_RDIF_HOPQ=4"], "rdif_h4")]
 SOURCES = sorted({u[0] for u in UNITS})
-HEADERS = ["kernels.cuh", "device_common.cuh", "fft_device.cuh", "stft_rdif.cuh", "stft_rdif_tm.cuh", "rdif_launch.h", "stream.cuh", "../../include/fftlines.h",
+HEADERS = ["kernels.cuh", "device_common.cuh", "fft_device.cuh", "stft_rdif.cuh", "stft_rdif_tm.cuh", "rdif_launch.h", "stream.cuh", "stream_carry.cuh", "../../include/fftlines.h",
            "../../include/fft_calculate.h", "../../include/beatDetector.h", "../../include/fftl_complex.h"]
 
 
@@ -27,7 +27,7 @@ def kernel_source_hash():
     bench.py can tell a capture of other code from a current one."""
     import hashlib
     h = hashlib.sha256()
-    for f in ("stft_rdif.cuh", "stft_rdif_tm.cuh", "fft_device.cuh", "device_common.cuh", "rdif_launch.cu", "rdif_launch.h"):
+    for f in ("stft_rdif.cuh", "stft_rdif_tm.cuh", "stream_carry.cuh", "fft_device.cuh", "device_common.cuh", "rdif_launch.cu", "rdif_launch.h"):
         with open(os.path.join(CSRC, f), "rb") as fh:
             h.update(fh.read())
     return h.hexdigest()[:16]

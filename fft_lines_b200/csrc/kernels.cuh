@@ -15,6 +15,7 @@
 //   synth_pcm_kernel   deterministic synthetic PCM.
 #pragma once
 #include "device_common.cuh"
+#include "stream_carry.cuh"
 
 namespace fftl {
 
@@ -249,13 +250,6 @@ constexpr int HB_STRIDE = FFTL_BEAT_SAMPLES + 2;
 //     one thread per bin k <= 128 (bins 129..160 are mirrors: the ring is real);
 //   - the peak scan of a frame is split over 8 lanes (20 bins each), 24 frames at a time;
 //   - AddBeatSample's 160-frame running sum is a difference of integer prefix sums.
-__device__ __forceinline__ float f64_to_f32(double x)
-{
-    float r; // plain round-to-nearest: --use_fast_math would turn a C cast into a flush-to-zero sequence
-    asm("cvt.rn.f32.f64 %0, %1;" : "=f"(r) : "d"(x));
-    return r;
-}
-
 constexpr int BEAT_FB = 96;
 
 // NF consecutive ring-transform updates of bin k (and, when EMIT, the bin's integer heights,

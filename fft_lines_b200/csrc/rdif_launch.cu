@@ -76,6 +76,7 @@ static cudaError_t launch_rdif_2k(int num_sms, const RdifParams& p, int channels
 template <int HOPQ, bool WIN>
 static cudaError_t launch_rdif_8k(int num_sms, const RdifParams& p, int channels, cudaStream_t st)
 {
+    if (p.sg_half == 3) return launch_rdif<8192, 4, HOPQ, WIN, 3, 16>(num_sms, p, channels, st); // the default smoothing width, unrolled
     return launch_rdif<8192, 4, HOPQ, WIN, -1, 16>(num_sms, p, channels, st);
 }
 
@@ -83,6 +84,7 @@ static cudaError_t launch_rdif_8k(int num_sms, const RdifParams& p, int channels
 template <bool WIN>
 static cudaError_t launch_rdif_16k(int num_sms, const RdifParams& p, int channels, cudaStream_t st)
 {
+    if (p.sg_half == 3) return launch_rdif<16384, 2, 0, WIN, 3, 32>(num_sms, p, channels, st); // the default smoothing width, unrolled
     return launch_rdif<16384, 2, 0, WIN, -1, 32>(num_sms, p, channels, st);
 }
 
@@ -148,7 +150,8 @@ cudaError_t FFTL_CAT(launch_rdif_h, FFTL_RDIF_HOPQ)(int n, bool win, int num_sms
 #endif
     }
 #if FFTL_RDIF_HOPQ == 0
-    // the own-samples variant is built with the run-time Savitzky-Golay width only
+    // the own-samples variant is built with the default Savitzky-Golay width unrolled and with the run-time width
+    if (p.sg_half == 3) return win ? launch_rdif_rows<0, true, 3>(num_sms, p, channels, st) : launch_rdif_rows<0, false, 3>(num_sms, p, channels, st);
     return win ? launch_rdif_rows<0, true, -1>(num_sms, p, channels, st) : launch_rdif_rows<0, false, -1>(num_sms, p, channels, st);
 #else
     return win ? launch_rdif_sg<FFTL_RDIF_HOPQ, true>(num_sms, p, channels, st) : launch_rdif_sg<FFTL_RDIF_HOPQ, false>(num_sms, p, channels, st);

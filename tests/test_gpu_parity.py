@@ -350,3 +350,18 @@ def test_tensor_memory_variant_is_race_free_under_repetition(oracle, lib):
             assert torch.equal(bars, ref_bars), "run %d" % it
             assert torch.equal(beat, ref_beat), "run %d" % it
         assert sp.tmem_launch_count == 40
+
+
+def test_tensor_memory_variant_without_beat_outputs(oracle, lib):
+    """want_beat=False (no band-energy / bass side outputs, aux pointers null): the tensor-memory kernel skips its band
+    energy and bass steps; the bars are the bits of the run with beat outputs."""
+    cfg = lib.extended_config(4096, 512, 200)
+    pcm = oracle.synth_pcm(3, 4096 + 300 * 512 + 77)
+    with lib.BatchedSpectrum(cfg) as sp:
+        a = sp.run(pcm)
+        n0 = sp.tmem_launch_count
+        b = sp.run(pcm, want_beat=False)
+        assert sp.tmem_launch_count > n0
+        c = sp.run(pcm, 5, 290, want_beat=False, want_i32=False)
+    assert (a["bars"] == b["bars"]).all() and (a["bars_i32"] == b["bars_i32"]).all()
+    assert (c["bars"] == a["bars"][:, 5:290]).all()

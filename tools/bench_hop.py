@@ -1,4 +1,4 @@
-"""quick_bench with a hop argument: python tools/scratch/qb_hop.py <hop> [interleaved]"""
+"""quick_bench with a hop argument: python tools/bench_hop.py <hop> [interleaved]"""
 import sys, time, torch
 sys.path.insert(0, ".")
 import fft_lines_b200 as F

@@ -14,9 +14,12 @@ CSRC = os.path.join(HERE, "csrc")
 LIB = os.path.join(HERE, "libfftlines_cuda.so")
 # translation units: (source, extra defines, object name).  The fast path's template instantiations are the
 # bulk of the compile time; one unit per hop variant lets them build in parallel.
+# The fast-path units use Blackwell's packed FP32 instructions (FFTL_F32X2, fft_device.cuh); the compiler folds the
+# swizzles and negations of the packed forms into operand modifiers only without flush-to-zero, hence -ftz=false there.
+F32X2 = ["-DFFTL_F32X2", "-ftz=false"]
 UNITS = [("api.cu", [], "api"),
-         ("rdif_launch.cu", ["-DFFTL_RDIF_HOPQ=0"], "rdif_h0"), ("rdif_launch.cu", ["-DFFTL_RDIF_HOPQ=1"], "rdif_h1"),
-         ("rdif_launch.cu", ["-DFFTL_RDIF_HOPQ=2"], "rdif_h2"), ("rdif_launch.cu", ["-DFFTL_RDIF_HOPQ=4"], "rdif_h4")]
+         ("rdif_launch.cu", ["-DFFTL_RDIF_HOPQ=0"] + F32X2, "rdif_h0"), ("rdif_launch.cu", ["-DFFTL_RDIF_HOPQ=1"] + F32X2, "rdif_h1"),
+         ("rdif_launch.cu", ["-DFFTL_RDIF_HOPQ=2"] + F32X2, "rdif_h2"), ("rdif_launch.cu", ["-DFFTL_RDIF_HOPQ=4"] + F32X2, "rdif_h4")]
 SOURCES = sorted({u[0] for u in UNITS})
 HEADERS = ["kernels.cuh", "device_common.cuh", "fft_device.cuh", "stft_rdif.cuh", "stft_rdif_tm.cuh", "rdif_launch.h", "stream.cuh", "stream_carry.cuh", "../../include/fftlines.h",
            "../../include/fft_calculate.h", "../../include/beatDetector.h", "../../include/fftl_complex.h"]
@@ -66,6 +69,8 @@ def build(force=False, verbose=False, extra=(), out=None, dev=False):
         def compile_unit(unit):
             src, defs, name = unit
             obj = os.path.join(tmp, name + ".o")
+            if "-DFFTL_NO_F32X2" in extra:  # developer A/B builds: the scalar forms
+                defs = [d for d in defs if d not in F32X2]
             cmd = common + list(extra) + defs + ["-c", os.path.join(CSRC, src), "-o", obj]
             r = subprocess.run(cmd, stdout=subprocess.PIPE, stderr=subprocess.STDOUT, text=True)
             return obj, cmd, r

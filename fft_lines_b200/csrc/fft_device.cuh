@@ -15,12 +15,34 @@
 
 namespace fftl {
 
+// Complex helpers.  FFTL_F32X2 (the fast-path translation units): Blackwell's packed FP32 instructions (FADD2 / FMUL2 /
+// FFMA2 on a 64-bit register pair, with half swizzle, per-half negate and scalar-broadcast operands) do the two halves
+// of a complex operation in one issue slot: complex add = 1 instruction, multiply = 2, a + w*b = 2.  Every packed form
+// performs exactly the two IEEE operations of its scalar twin below (same operands, same roundings), so the results
+// are bit-identical; the compiler folds the swizzles and negations into operand modifiers only without flush-to-zero
+// (those units are built with -ftz=false).
+#ifdef FFTL_F32X2
+__device__ __forceinline__ float2 cadd(float2 a, float2 b) { return __fadd2_rn(a, b); }
+__device__ __forceinline__ float2 csub(float2 a, float2 b) { return __fadd2_rn(a, make_float2(-b.x, -b.y)); }
+__device__ __forceinline__ float2 cmul(float2 a, float2 b)
+{
+    const float2 t = __fmul2_rn(make_float2(a.y, a.y), make_float2(b.y, b.x));
+    return __ffma2_rn(make_float2(a.x, a.x), b, make_float2(-t.x, t.y));
+}
+// a - i b, a + i b
+__device__ __forceinline__ float2 csub_i(float2 a, float2 b) { return __fadd2_rn(a, make_float2(b.y, -b.x)); }
+__device__ __forceinline__ float2 cadd_i(float2 a, float2 b) { return __fadd2_rn(a, make_float2(-b.y, b.x)); }
+#else
 __device__ __forceinline__ float2 cadd(float2 a, float2 b) { return make_float2(a.x + b.x, a.y + b.y); }
 __device__ __forceinline__ float2 csub(float2 a, float2 b) { return make_float2(a.x - b.x, a.y - b.y); }
 __device__ __forceinline__ float2 cmul(float2 a, float2 b)
 {
     return make_float2(fmaf(a.x, b.x, -a.y * b.y), fmaf(a.x, b.y, a.y * b.x));
 }
+// a - i b, a + i b
+__device__ __forceinline__ float2 csub_i(float2 a, float2 b) { return make_float2(a.x + b.y, a.y - b.x); }
+__device__ __forceinline__ float2 cadd_i(float2 a, float2 b) { return make_float2(a.x - b.y, a.y + b.x); }
+#endif
 // a * (-i)
 __device__ __forceinline__ float2 cmul_mi(float2 a) { return make_float2(a.y, -a.x); }
 
@@ -34,23 +56,41 @@ __device__ __forceinline__ void dft2(float2& a, float2& b)
 // forward 4-point DFT in place, natural order
 __device__ __forceinline__ void dft4(float2& a0, float2& a1, float2& a2, float2& a3)
 {
-    float2 t0 = cadd(a0, a2), t1 = csub(a0, a2), t2 = cadd(a1, a3), t3 = cmul_mi(csub(a1, a3));
+    float2 t0 = cadd(a0, a2), t1 = csub(a0, a2), t2 = cadd(a1, a3), d = csub(a1, a3);
     a0 = cadd(t0, t2);
     a2 = csub(t0, t2);
-    a1 = cadd(t1, t3);
-    a3 = csub(t1, t3);
+    a1 = csub_i(t1, d);
+    a3 = cadd_i(t1, d);
+}
+
+// sqrt.approx.ftz.f32 (one MUFU): what --use_fast_math makes of sqrtf; spelled out because the fast-path units are
+// built without flush-to-zero (FFTL_F32X2), where sqrtf would become the slower denormal-aware sequence
+__device__ __forceinline__ float sqrt_approx_ftz(float x)
+{
+    float r;
+    asm("sqrt.approx.ftz.f32 %0, %1;" : "=f"(r) : "f"(x));
+    return r;
 }
 
 #define FFTL_SQRT1_2 0.70710678118654752440f
 #define FFTL_COS_PI_8 0.92387953251128675613f
 #define FFTL_SIN_PI_8 0.38268343236508977173f
 
+#ifdef FFTL_F32X2
+// multiply by W8^1 = (1-i)/sqrt2, W8^3 = (-1-i)/sqrt2
+__device__ __forceinline__ float2 cmul_w8_1(float2 a) { return __fmul2_rn(__fadd2_rn(a, make_float2(a.y, -a.x)), make_float2(FFTL_SQRT1_2, FFTL_SQRT1_2)); }
+__device__ __forceinline__ float2 cmul_w8_3(float2 a) { return __fmul2_rn(__fadd2_rn(make_float2(a.y, -a.y), make_float2(-a.x, -a.x)), make_float2(FFTL_SQRT1_2, FFTL_SQRT1_2)); }
+// W16^1 = (c,-s), W16^3 = (s,-c), W16^9 = -W16^1   (c = cos(pi/8), s = sin(pi/8))
+__device__ __forceinline__ float2 cmul_w16_1(float2 a) { return __ffma2_rn(a, make_float2(FFTL_COS_PI_8, FFTL_COS_PI_8), __fmul2_rn(make_float2(a.y, -a.x), make_float2(FFTL_SIN_PI_8, FFTL_SIN_PI_8))); }
+__device__ __forceinline__ float2 cmul_w16_3(float2 a) { return __ffma2_rn(a, make_float2(FFTL_SIN_PI_8, FFTL_SIN_PI_8), __fmul2_rn(make_float2(a.y, -a.x), make_float2(FFTL_COS_PI_8, FFTL_COS_PI_8))); }
+#else
 // multiply by W8^1 = (1-i)/sqrt2, W8^3 = (-1-i)/sqrt2
 __device__ __forceinline__ float2 cmul_w8_1(float2 a) { return make_float2((a.x + a.y) * FFTL_SQRT1_2, (a.y - a.x) * FFTL_SQRT1_2); }
 __device__ __forceinline__ float2 cmul_w8_3(float2 a) { return make_float2((a.y - a.x) * FFTL_SQRT1_2, -(a.x + a.y) * FFTL_SQRT1_2); }
 // W16^1 = (c,-s), W16^3 = (s,-c), W16^9 = -W16^1   (c = cos(pi/8), s = sin(pi/8))
 __device__ __forceinline__ float2 cmul_w16_1(float2 a) { return make_float2(fmaf(a.x, FFTL_COS_PI_8, a.y * FFTL_SIN_PI_8), fmaf(a.y, FFTL_COS_PI_8, -a.x * FFTL_SIN_PI_8)); }
 __device__ __forceinline__ float2 cmul_w16_3(float2 a) { return make_float2(fmaf(a.x, FFTL_SIN_PI_8, a.y * FFTL_COS_PI_8), fmaf(a.y, FFTL_SIN_PI_8, -a.x * FFTL_COS_PI_8)); }
+#endif
 __device__ __forceinline__ float2 cmul_w16_9(float2 a) { float2 t = cmul_w16_1(a); return make_float2(-t.x, -t.y); }
 
 // In-register forward DFT of R points.  Output X[k] ends up in register
@@ -106,11 +146,20 @@ template <> struct Radix<16> {
 // ---- radix-16 with the multiplies folded into the butterflies (fast path only) ----------------------
 // a + w*b with both products as fused multiply-adds (4 FFMA), and the matching difference as 2a - (a + w*b)
 // (2 FFMA): a twiddled radix-2 costs 6 instructions instead of 8.
+#ifdef FFTL_F32X2
+__device__ __forceinline__ float2 cfma(float2 a, float2 w, float2 b) // a + w*b
+{
+    const float2 t = __ffma2_rn(make_float2(b.y, b.x), make_float2(-w.y, w.y), a);
+    return __ffma2_rn(make_float2(w.x, w.x), b, t);
+}
+__device__ __forceinline__ float2 ctwice_minus(float2 a, float2 t) { return __ffma2_rn(make_float2(2.0f, 2.0f), a, make_float2(-t.x, -t.y)); }
+#else
 __device__ __forceinline__ float2 cfma(float2 a, float2 w, float2 b) // a + w*b
 {
     return make_float2(fmaf(w.x, b.x, fmaf(-w.y, b.y, a.x)), fmaf(w.x, b.y, fmaf(w.y, b.x, a.y)));
 }
 __device__ __forceinline__ float2 ctwice_minus(float2 a, float2 t) { return make_float2(fmaf(2.0f, a.x, -t.x), fmaf(2.0f, a.y, -t.y)); }
+#endif
 
 // forward 4-point DFT of (a0, w1*b1, w2*b2, w3*b3), natural order; a0 comes in already multiplied
 __device__ __forceinline__ void dft4_tw(float2& a0, float2& b1, float2& b2, float2& b3, float2 w1, float2 w2, float2 w3)
@@ -120,8 +169,8 @@ __device__ __forceinline__ void dft4_tw(float2& a0, float2& b1, float2& b2, floa
     const float2 t2 = cfma(a1, w3, b3), d = ctwice_minus(a1, t2);    // a1 +- w3 b3
     a0 = cadd(t0, t2);
     b2 = csub(t0, t2);
-    b1 = make_float2(t1.x + d.y, t1.y - d.x);                        // t1 - i d
-    b3 = make_float2(t1.x - d.y, t1.y + d.x);                        // t1 + i d
+    b1 = csub_i(t1, d);                                              // t1 - i d
+    b3 = cadd_i(t1, d);                                              // t1 + i d
 }
 
 // Radix<16>::run with (TW) every input but v[0] first multiplied by tw[r]; same output order.
@@ -148,8 +197,8 @@ template <bool TW> __device__ __forceinline__ void radix16_fused(float2* v, cons
         const float2 t2 = cfma(a1, W3, v[7]), d = ctwice_minus(a1, t2);
         v[4] = cadd(t0, t2);
         v[6] = csub(t0, t2);
-        v[5] = make_float2(t1.x + d.y, t1.y - d.x);
-        v[7] = make_float2(t1.x - d.y, t1.y + d.x);
+        v[5] = csub_i(t1, d);
+        v[7] = cadd_i(t1, d);
     }
     v[9] = cmul_w8_1(v[9]);    // k2 = 2: (1, W16^2, W16^4, W16^6)
     v[10] = cmul_mi(v[10]);
@@ -162,8 +211,8 @@ template <bool TW> __device__ __forceinline__ void radix16_fused(float2* v, cons
         const float2 t2 = cfma(a1, W9, v[15]), d = ctwice_minus(a1, t2);
         v[12] = cadd(t0, t2);
         v[14] = csub(t0, t2);
-        v[13] = make_float2(t1.x + d.y, t1.y - d.x);
-        v[15] = make_float2(t1.x - d.y, t1.y + d.x);
+        v[13] = csub_i(t1, d);
+        v[15] = cadd_i(t1, d);
     }
 }
 

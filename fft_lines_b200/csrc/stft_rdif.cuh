@@ -577,7 +577,7 @@ __global__ void __launch_bounds__(RdifShape<N, F>::THREADS, MINB) stft_bars_rdif
                     const int kk = Radix<16>::out_index(rr);
                     const int c = kk < 8 ? kk : 15 - kk; // 256-bin row of this output
                     if (c < ROWS) {                      // rows no bar reads are neither computed nor stored
-                        float mag = sqrtf(fmaf(v[rr].x, v[rr].x, v[rr].y * v[rr].y));
+                        float mag = sqrt_approx_ftz(fmaf(v[rr].x, v[rr].x, v[rr].y * v[rr].y));
                         if (kk < 8) lo_base[2 * 272 * c] = mag;
                         else hi_base[2 * 272 * c] = mag;
                     }
@@ -601,7 +601,7 @@ __global__ void __launch_bounds__(RdifShape<N, F>::THREADS, MINB) stft_bars_rdif
                     float ar = v[rr].x + pr_, ai = v[rr].y - pi_; // 2 * Xa
                     float br = v[rr].x - pr_, bi = v[rr].y + pi_; // 2i * Xb
                     int bin = 16 * (j + 16 * kk) + (hw ? 8 : 0);
-                    const float2 mm = make_float2(0.5f * sqrtf(fmaf(ar, ar, ai * ai)), 0.5f * sqrtf(fmaf(br, br, bi * bi)));
+                    const float2 mm = make_float2(0.5f * sqrt_approx_ftz(fmaf(ar, ar, ai * ai)), 0.5f * sqrt_approx_ftz(fmaf(br, br, bi * bi)));
                     mg2[pad_index(bin)] = mm;
                 }
                 if (self && ROWS >= 8) {
@@ -651,7 +651,7 @@ __global__ void __launch_bounds__(RdifShape<N, F>::THREADS, MINB) stft_bars_rdif
                         const int c = kk < HALF ? kk : R2 - 1 - kk;
                         if (c < ROWS) {
                             const float2 z = v[R2 * tt + rr];
-                            const float mag = sqrtf(fmaf(z.x, z.x, z.y * z.y));
+                            const float mag = sqrt_approx_ftz(fmaf(z.x, z.x, z.y * z.y));
                             if (kk < HALF) lo_base[2 * 272 * c] = mag;
                             else hi_base[2 * 272 * c] = mag;
                         }
@@ -681,7 +681,7 @@ __global__ void __launch_bounds__(RdifShape<N, F>::THREADS, MINB) stft_bars_rdif
                         float ar = z.x + pr_, ai = z.y - pi_; // 2 * Xa
                         float br = z.x - pr_, bi = z.y + pi_; // 2i * Xb
                         const int bin = 16 * ((j + SUBG * tt) + 16 * kk) + (hw ? 8 : 0);
-                        mg2[pad_index(bin)] = make_float2(0.5f * sqrtf(fmaf(ar, ar, ai * ai)), 0.5f * sqrtf(fmaf(br, br, bi * bi)));
+                        mg2[pad_index(bin)] = make_float2(0.5f * sqrt_approx_ftz(fmaf(ar, ar, ai * ai)), 0.5f * sqrt_approx_ftz(fmaf(br, br, bi * bi)));
                     }
                 }
                 if (self && ROWS >= HALF) {
@@ -733,8 +733,8 @@ __global__ void __launch_bounds__(RdifShape<N, F>::THREADS, MINB) stft_bars_rdif
                 for (int tt = 0; tt < 8; tt++) {
                     const int m = j + 32 * tt;
                     const float2 z0 = v[2 * tt], z1 = v[2 * tt + 1];
-                    mg[2 * (k0 + 17 * m)] = sqrtf(fmaf(z0.x, z0.x, z0.y * z0.y));
-                    mg[2 * ((16 - k0) + 17 * (255 - m))] = sqrtf(fmaf(z1.x, z1.x, z1.y * z1.y));
+                    mg[2 * (k0 + 17 * m)] = sqrt_approx_ftz(fmaf(z0.x, z0.x, z0.y * z0.y));
+                    mg[2 * ((16 - k0) + 17 * (255 - m))] = sqrt_approx_ftz(fmaf(z1.x, z1.x, z1.y * z1.y));
                 }
             } else {
                 // packed slot (hw 0: residue 0, partner m' = 512-m; hw 1: residue 8, partner m' = 511-m); bins m < 256
@@ -755,7 +755,7 @@ __global__ void __launch_bounds__(RdifShape<N, F>::THREADS, MINB) stft_bars_rdif
                     float ar = z.x + pr_, ai = z.y - pi_; // 2 * Xa
                     float br = z.x - pr_, bi = z.y + pi_; // 2i * Xb
                     const int bin = 16 * (j + 32 * tt) + (hw ? 8 : 0);
-                    mg2[pad_index(bin)] = make_float2(0.5f * sqrtf(fmaf(ar, ar, ai * ai)), 0.5f * sqrtf(fmaf(br, br, bi * bi)));
+                    mg2[pad_index(bin)] = make_float2(0.5f * sqrt_approx_ftz(fmaf(ar, ar, ai * ai)), 0.5f * sqrt_approx_ftz(fmaf(br, br, bi * bi)));
                 }
                 if (self) mg2[pad_index(N / 2)] = make_float2(fabsf(v[1].x), fabsf(v[1].y)); // m = 256: Xa[N/2] + i Xb[N/2], both real
             }
@@ -900,7 +900,7 @@ __global__ void __launch_bounds__(RdifShape<N, F>::THREADS, MINB) stft_bars_rdif
                     for (int rr = 0; rr < 4; rr++) {
                         const int m = j + 32 * tt + 256 * rr;
                         const float2 z = v[4 * tt + rr];
-                        const float mag = sqrtf(fmaf(z.x, z.x, z.y * z.y));
+                        const float mag = sqrt_approx_ftz(fmaf(z.x, z.x, z.y * z.y));
                         if (rr < 2) mg[2 * (k0 + 17 * m)] = mag;
                         else mg[2 * ((16 - k0) + 17 * (1023 - m))] = mag;
                     }
@@ -926,7 +926,7 @@ __global__ void __launch_bounds__(RdifShape<N, F>::THREADS, MINB) stft_bars_rdif
                         float ar = z.x + pr_, ai = z.y - pi_; // 2 * Xa
                         float br = z.x - pr_, bi = z.y + pi_; // 2i * Xb
                         const int bin = 16 * (j + 32 * tt + 256 * rr) + (hw ? 8 : 0);
-                        mg2[pad_index(bin)] = make_float2(0.5f * sqrtf(fmaf(ar, ar, ai * ai)), 0.5f * sqrtf(fmaf(br, br, bi * bi)));
+                        mg2[pad_index(bin)] = make_float2(0.5f * sqrt_approx_ftz(fmaf(ar, ar, ai * ai)), 0.5f * sqrt_approx_ftz(fmaf(br, br, bi * bi)));
                     }
                 }
                 if (self) mg2[pad_index(N / 2)] = make_float2(fabsf(v[2].x), fabsf(v[2].y)); // m = 512: Xa[N/2] + i Xb[N/2], both real

@@ -366,7 +366,7 @@ __global__ void __launch_bounds__(RdifTmShape<N>::THREADS, RdifTmShape<N>::MINB)
                         const int kk = Radix<R2>::out_index(rr);
                         const int c = kk < HALF ? kk : R2 - 1 - kk; // 256-bin row of this output
                         const float2 z = v[R2 * tt + rr];
-                        if (c < RW) mg[2 * RW * tt + (kk < HALF ? c : RW + c)] = sqrtf(fmaf(z.x, z.x, z.y * z.y));
+                        if (c < RW) mg[2 * RW * tt + (kk < HALF ? c : RW + c)] = sqrt_approx_ftz(fmaf(z.x, z.x, z.y * z.y));
                     }
             } else {
                 // packed slot (hw 0: residue 0, partner m' = M-m; hw 1: residue 8, partner m' = M-1-m): the partner of (jj, kk) is
@@ -389,10 +389,10 @@ __global__ void __launch_bounds__(RdifTmShape<N>::THREADS, RdifTmShape<N>::MINB)
                             pi_ = own.y;
                         }
                         const float2 z = v[R2 * tt + rr];
-                        float ar = z.x + pr_, ai = z.y - pi_; // 2 * Xa
-                        float br = z.x - pr_, bi = z.y + pi_; // 2i * Xb
-                        mg[2 * RW * tt + 2 * kk] = 0.5f * sqrtf(fmaf(ar, ar, ai * ai));
-                        mg[2 * RW * tt + 2 * kk + 1] = 0.5f * sqrtf(fmaf(br, br, bi * bi));
+                        const float2 xa = cadd(z, make_float2(pr_, -pi_)); // 2 * Xa
+                        const float2 xb = cadd(z, make_float2(-pr_, pi_)); // 2i * Xb
+                        mg[2 * RW * tt + 2 * kk] = 0.5f * sqrt_approx_ftz(fmaf(xa.x, xa.x, xa.y * xa.y));
+                        mg[2 * RW * tt + 2 * kk + 1] = 0.5f * sqrt_approx_ftz(fmaf(xb.x, xb.x, xb.y * xb.y));
                     }
             }
         };

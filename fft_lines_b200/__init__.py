@@ -16,10 +16,10 @@ from ._capi import (FftlConfig, FftlBeat, FftLinesError, WINDOW_RECT, WINDOW_HAN
 from .stft import (BatchedSpectrum, reference_config, extended_config, build_bins, build_sg, BEAT_DTYPE,
                    device_count, synth_pcm_device, PinnedArray, measure_fp32_peak)
 from .stream import StreamingSpectrum
-from ._capi import MOVE_EXACT, MOVE_REFERENCE
+from ._capi import MOVE_EXACT, MOVE_REFERENCE, TICK_AUTO, TICK_THREE_LAUNCHES
 from . import fft_calculate, beat_detector, sharding, sinks
 
 __all__ = ["FftlConfig", "FftlBeat", "FftLinesError", "BatchedSpectrum", "reference_config",
            "extended_config", "build_bins", "build_sg", "BEAT_DTYPE", "device_count", "synth_pcm_device",
-           "PinnedArray", "measure_fp32_peak", "StreamingSpectrum", "MOVE_EXACT", "MOVE_REFERENCE", "fft_calculate", "beat_detector", "sharding", "sinks", "WINDOW_RECT", "WINDOW_HANN",
+           "PinnedArray", "measure_fp32_peak", "StreamingSpectrum", "MOVE_EXACT", "MOVE_REFERENCE", "TICK_AUTO", "TICK_THREE_LAUNCHES", "fft_calculate", "beat_detector", "sharding", "sinks", "WINDOW_RECT", "WINDOW_HANN",
            "BINNING_LINEAR", "BINNING_LOG", "BEAT_SAMPLES", "TEMPO_RING", "LIB_PATH"]

@@ -15,6 +15,7 @@ BINNING_LINEAR, BINNING_LOG = 0, 1
 BEAT_SAMPLES, TEMPO_RING = 160, 256
 MOVE_EXACT, MOVE_REFERENCE = 0, 1
 KERNEL_AUTO, KERNEL_GENERIC, KERNEL_FAST_REGISTERS = 0, 1, 2
+TICK_AUTO, TICK_THREE_LAUNCHES = 0, 1
 
 
 class FftlConfig(C.Structure):
@@ -57,7 +58,7 @@ EXPORTED_FUNCTIONS = {
         "fftl_stft_sample_span", "fftl_stft_run_device", "fftl_stft_run_device_span", "fftl_stft_run", "fftl_stft_launch_count",
         "fftl_stft_fast_launch_count", "fftl_stft_tmem_launch_count", "fftl_stft_set_kernel", "fftl_stft_timing",
         "fftl_stream_create", "fftl_stream_destroy", "fftl_stream_reset", "fftl_stream_push_device",
-        "fftl_stream_push", "fftl_stream_push_device_f32", "fftl_stream_launch_count", "fftl_stream_set_history", "fftl_stream_history_device",
+        "fftl_stream_push", "fftl_stream_push_device_f32", "fftl_stream_launch_count", "fftl_stream_set_tick_kernel", "fftl_stream_fused_tick_count", "fftl_stream_set_history", "fftl_stream_history_device",
         "fftl_stream_waveform_device", "fftl_settings_default", "fftl_settings_parse", "fftl_settings_format",
         "fftl_settings_to_config", "fftl_color_index", "fftl_led_bytes_device", "fftl_marker_sweep_device",
         "fftl_host_alloc", "fftl_host_free", "fftl_synth_pcm_device", "fftl_measure_fp32_peak", "fftl_last_error",
@@ -131,6 +132,10 @@ def lib():
     L.fftl_stream_waveform_device.argtypes = [vp, C.c_int32, C.c_float, C.c_float, vp, vp]
     L.fftl_stream_launch_count.argtypes = [vp]
     L.fftl_stream_launch_count.restype = C.c_int64
+    L.fftl_stream_fused_tick_count.argtypes = [vp]
+    L.fftl_stream_fused_tick_count.restype = C.c_int64
+    L.fftl_stream_set_tick_kernel.argtypes = [vp, C.c_int32]
+    L.fftl_stream_set_tick_kernel.restype = C.c_int
     L.fftl_settings_default.argtypes = [C.POINTER(FftlSettings)]
     L.fftl_settings_default.restype = None
     L.fftl_settings_parse.argtypes = [C.c_char_p, C.c_int64, C.POINTER(FftlSettings)]

@@ -21,7 +21,7 @@ UNITS = [("api.cu", [], "api"),
          ("rdif_launch.cu", ["-DFFTL_RDIF_HOPQ=0"] + F32X2, "rdif_h0"), ("rdif_launch.cu", ["-DFFTL_RDIF_HOPQ=1"] + F32X2, "rdif_h1"),
          ("rdif_launch.cu", ["-DFFTL_RDIF_HOPQ=2"] + F32X2, "rdif_h2"), ("rdif_launch.cu", ["-DFFTL_RDIF_HOPQ=4"] + F32X2, "rdif_h4")]
 SOURCES = sorted({u[0] for u in UNITS})
-HEADERS = ["kernels.cuh", "device_common.cuh", "fft_device.cuh", "stft_rdif.cuh", "stft_rdif_tm.cuh", "rdif_launch.h", "stream.cuh", "stream_carry.cuh", "../../include/fftlines.h",
+HEADERS = ["kernels.cuh", "device_common.cuh", "fft_device.cuh", "stft_rdif.cuh", "stft_rdif_tm.cuh", "rdif_launch.h", "stream.cuh", "stream_tick.cuh", "stream_carry.cuh", "../../include/fftlines.h",
            "../../include/fft_calculate.h", "../../include/beatDetector.h", "../../include/fftl_complex.h"]
 
 

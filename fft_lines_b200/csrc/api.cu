@@ -15,6 +15,7 @@
 #include "kernels.cuh"
 #include "rdif_launch.h"
 #include "stream.cuh"
+#include "stream_tick.cuh"
 #include "../../include/fft_calculate.h"
 #include "../../include/beatDetector.h"
 
@@ -934,7 +935,8 @@ struct fftl_stream {
     fftl_beat* d_beat;
     float* d_hist;          // [streams][hist_depth][bars] or NULL
     int hist_depth;
-    int64_t launches;
+    int tick_kernel;        // FFTL_TICK_AUTO / FFTL_TICK_THREE_LAUNCHES
+    int64_t launches, fused_ticks;
 };
 
 extern "C" void fftl_stream_destroy(fftl_stream* s)
@@ -1074,6 +1076,22 @@ extern "C" int fftl_stream_create(const fftl_config* cfg, int32_t streams, int32
 }
 
 extern "C" int64_t fftl_stream_launch_count(const fftl_stream* s) { return s ? s->launches : 0; }
+extern "C" int64_t fftl_stream_fused_tick_count(const fftl_stream* s) { return s ? s->fused_ticks : 0; }
+extern "C" int fftl_stream_set_tick_kernel(fftl_stream* s, int32_t which)
+{
+    if (!s) return set_error(FFTL_ERR_ARG, "stream handle is NULL");
+    if (which != FFTL_TICK_AUTO && which != FFTL_TICK_THREE_LAUNCHES) return set_error(FFTL_ERR_ARG, "unknown tick kernel selection %d", which);
+    s->tick_kernel = which;
+    return FFTL_OK;
+}
+
+// One kernel per tick (stream_tick.cuh): n = 1024 / 2048, exact window move.
+template <int N>
+static cudaError_t launch_stream_tick(const StftParams& p, const StreamTickParams& k, const StreamCarry& q, int sg_half, cudaStream_t st)
+{
+    stream_tick_kernel<N><<<(k.streams + 1) / 2, N / 4, stream_tick_smem<N>(p.bars_n, sg_half), st>>>(p, k, q);
+    return cudaGetLastError();
+}
 
 extern "C" int fftl_stream_push_device(fftl_stream* s, const int16_t* fresh, int32_t count, int64_t stride, float* bars, int32_t* bars_i32,
                                        fftl_beat* beat, void* cuda_stream)
@@ -1090,6 +1108,60 @@ extern "C" int fftl_stream_push_device(fftl_stream* s, const int16_t* fresh, int
         if (s->move_mode == FFTL_MOVE_REFERENCE) return set_error(FFTL_ERR_ARG, "count > n is undefined for the reference's MoveArray");
         fresh += count - c.n;
         count = c.n;
+    }
+    if (s->tick_kernel == FFTL_TICK_AUTO && s->move_mode == FFTL_MOVE_EXACT && (c.n == 1024 || c.n == 2048) &&
+        stream_tick_smem<2048>(c.bars, c.sg_half) <= 48 * 1024) {
+        StftParams p;
+        memset(&p, 0, sizeof(p));
+        p.window = h->d_window;
+        p.tw = h->d_tw;
+        p.lo = h->d_lo;
+        p.hi = h->d_hi;
+        p.bar_inv = h->d_bar_inv;
+        p.sg = h->d_sg;
+        p.bars = bars;
+        p.bars_i32 = bars_i32;
+        p.aux_w = h->d_aux;
+        p.aux_bass = h->d_aux + s->streams;
+        p.bars_n = c.bars;
+        p.sg_half = h->d_sg ? c.sg_half : 0;
+        p.strict = c.strict_int;
+        p.bass_bin = c.bass_bin;
+        for (int i = 0; i < 4; i++) p.beat_bars[i] = c.beat_bars[i];
+        p.zoom = c.zoom;
+        p.circle_add = c.circle ? 10.0f : 0.0f; // fft_lines.c:204-207
+        StreamTickParams k;
+        k.window = s->d_window;
+        k.fresh = fresh;
+        k.fresh_stride = stride;
+        k.count = count;
+        k.streams = s->streams;
+        StreamCarry cq;
+        cq.aux_w = p.aux_w;
+        cq.aux_bass = p.aux_bass;
+        cq.w_ring = s->d_w_ring;
+        cq.w_sum = s->d_w_sum;
+        cq.tempo_ring = s->d_tempo_ring;
+        cq.x = s->d_tempo_x;
+        cq.tw256d = h->d_tw256d;
+        cq.state = s->d_state;
+        cq.out = beat ? beat : s->d_beat;
+        cq.streams = s->streams;
+        cq.n_times_dt = (float)c.n * dt;
+        cq.strict = c.strict_int;
+        cq.finish = s->d_hist ? 0 : 1; // the history push, when enabled, is the last kernel
+        CUDA_TRY(c.n == 1024 ? launch_stream_tick<1024>(p, k, cq, p.sg_half, st) : launch_stream_tick<2048>(p, k, cq, p.sg_half, st));
+        s->launches++;
+        s->fused_ticks++;
+        if (s->d_hist) {
+            long long total = (long long)s->streams * c.bars;
+            long long blocks = (total + 255) / 256;
+            if (blocks > 4096) blocks = 4096;
+            stream_history_push_kernel<<<(unsigned)blocks, 256, 0, st>>>(s->d_hist, bars, s->d_state, s->streams, s->hist_depth, c.bars);
+            CUDA_TRY(cudaGetLastError());
+            s->launches++;
+        }
+        return FFTL_OK;
     }
     if (s->move_mode != FFTL_MOVE_REFERENCE && (count & 7) == 0 && (c.n & 7) == 0 && (stride & 7) == 0 && ((uintptr_t)fresh & 15) == 0)
         stream_slide_vec_kernel<<<s->streams, 256, 0, st>>>(s->d_window, fresh, c.n, count, stride);

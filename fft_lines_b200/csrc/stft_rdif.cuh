@@ -189,7 +189,7 @@ __device__ __forceinline__ float2 ldg_pinned(const float2* p)
 }
 
 // Savitzky-Golay over the raw bar vector for F frames at once; TAPS < 0: run-time width.
-template <int F, int TAPS>
+template <int F, int TAPS, bool PK = false>
 __device__ __forceinline__ void sg_apply(const float* cf, const float* rw, int m, float* y)
 {
 #pragma unroll
@@ -200,8 +200,7 @@ __device__ __forceinline__ void sg_apply(const float* cf, const float* rw, int m
             const float c = cf[k];
             float u[F];
             FrameVec<F>::load(rw + k * F, u);
-#pragma unroll
-            for (int f = 0; f < F; f++) y[f] = fmaf(c, u[f], y[f]);
+            vec_fma<F, PK>(c, u, y);
         }
     } else {
 #pragma unroll 1
@@ -209,8 +208,7 @@ __device__ __forceinline__ void sg_apply(const float* cf, const float* rw, int m
             const float c = cf[k];
             float u[F];
             FrameVec<F>::load(rw + k * F, u);
-#pragma unroll
-            for (int f = 0; f < F; f++) y[f] = fmaf(c, u[f], y[f]);
+            vec_fma<F, PK>(c, u, y);
         }
     }
 }
@@ -256,7 +254,7 @@ struct TileCursor {
 // (sorting it by length was measured: 5 % slower from bank conflicts).
 #define FFTL_SEG_PACK(padded_lo, cnt, idx) ((padded_lo) | ((cnt) << 14) | ((idx) << 19))
 
-template <int F, int MAGS, int K> __device__ __forceinline__ void seg_steps(const float2* m0, int cnt, float* acc)
+template <int F, int MAGS, int K, bool PK> __device__ __forceinline__ void seg_steps(const float2* m0, int cnt, float* acc)
 {
 #pragma unroll
     for (int i = 0; i < K; i++) {
@@ -264,8 +262,8 @@ template <int F, int MAGS, int K> __device__ __forceinline__ void seg_steps(cons
 #pragma unroll
             for (int pr = 0; pr < F / 2; pr++) {
                 const float2 a = m0[pr * MAGS + i];
-                acc[2 * pr] += a.x;
-                acc[2 * pr + 1] += a.y;
+                const float u[2] = {a.x, a.y};
+                vec_add<2, PK>(acc + 2 * pr, u);
             }
         }
     }
@@ -274,7 +272,7 @@ template <int F, int MAGS, int K> __device__ __forceinline__ void seg_steps(cons
 // Tail, first step: per-segment sums of the magnitudes of the tile's F frames.  Segments are at most 8 bins
 // long and never cross a multiple of 16, so one is at most 8 consecutive padded positions.  Every thread of
 // the calling group must take part (warp shuffles); nthreads is a multiple of 32.
-template <int F, int MAGS>
+template <int F, int MAGS, bool PK = false>
 __device__ __forceinline__ void rdif_segment_sums(const int* t_seg, const float2* mags, float* segsum, int nseg, int t, int nthreads)
 {
     for (int base = 0; base < nseg; base += nthreads) {
@@ -288,9 +286,9 @@ __device__ __forceinline__ void rdif_segment_sums(const int* t_seg, const float2
         // the low bars are 1-2 bins wide: their warps take the short form; segments longer than 8 bins exist only
         // where the host needed them to fit the work list into one pass
         const int longest = __reduce_max_sync(0xffffffffu, cnt);
-        if (longest <= 2) seg_steps<F, MAGS, 2>(m0, cnt, acc);
-        else if (longest <= 8) seg_steps<F, MAGS, 8>(m0, cnt, acc);
-        else seg_steps<F, MAGS, 16>(m0, cnt, acc);
+        if (longest <= 2) seg_steps<F, MAGS, 2, PK>(m0, cnt, acc);
+        else if (longest <= 8) seg_steps<F, MAGS, 8, PK>(m0, cnt, acc);
+        else seg_steps<F, MAGS, 16, PK>(m0, cnt, acc);
         if (cnt) FrameVec<F>::store(segsum + (int)((unsigned)sd >> 19) * F, acc);
     }
 }
@@ -308,7 +306,7 @@ __device__ __forceinline__ void sg_row(int b, int B, int w, int& row, int& base)
 // `nthreads` threads (this one is number t).  The float multiply and add are the explicit _rn forms so
 // that the fast and the careful branch round alike (a frame can sit in an edge tile of one shard and in
 // an interior tile of the full run).
-template <int F, int SGW>
+template <int F, int SGW, bool PK = false>
 __device__ __forceinline__ void rdif_emit_bars(const RdifParams& p, const float* raw, const float* t_sg, int t, int nthreads, bool interior, long long o0,
                                                long long f0)
 {
@@ -323,11 +321,12 @@ __device__ __forceinline__ void rdif_emit_bars(const RdifParams& p, const float*
             else {
                 int row, base;
                 sg_row(b, B, w, row, base);
-                sg_apply<F, (SGW > 0 ? 2 * SGW + 1 : -1)>(t_sg + row * m, raw + base * F, m, y);
+                sg_apply<F, (SGW > 0 ? 2 * SGW + 1 : -1), PK>(t_sg + row * m, raw + base * F, m, y);
             }
             float* ob = p.bars + (o0 + b);
+            vec_scale<F, PK>(y, p.zoom);
 #pragma unroll
-            for (int f = 0; f < F; f++) ob[f * B] = __fadd_rn(__fmul_rn(y[f], p.zoom), p.circle_add);
+            for (int f = 0; f < F; f++) ob[f * B] = __fadd_rn(y[f], p.circle_add);
         }
         return;
     }
@@ -343,13 +342,13 @@ __device__ __forceinline__ void rdif_emit_bars(const RdifParams& p, const float*
         else {
             int row, base;
             sg_row(b, B, w, row, base);
-            sg_apply<F, (SGW > 0 ? 2 * SGW + 1 : -1)>(t_sg + row * m, raw + base * F, m, y);
+            sg_apply<F, (SGW > 0 ? 2 * SGW + 1 : -1), PK>(t_sg + row * m, raw + base * F, m, y);
         }
         float* ob = p.bars + (o0 + b);
         int* oi = p.bars_i32 ? p.bars_i32 + (o0 + b) : nullptr;
+        vec_scale<F, PK>(y, p.zoom);
 #pragma unroll
         for (int f = 0; f < F; f++) {
-            y[f] = __fmul_rn(y[f], p.zoom);
             if (f >= e_lo && f < e_hi) {
                 ob[f * B] = __fadd_rn(y[f], p.circle_add);
                 if (oi) oi[f * B] = wrap_add(trunc_i32(y[f], p.strict), cadd);
@@ -411,6 +410,7 @@ __global__ void __launch_bounds__(RdifShape<N, F>::THREADS, MINB) stft_bars_rdif
     using Sh = RdifShape<N, F>;
     constexpr int M = Sh::M, SUBG = Sh::SUBG, SLOT = Sh::SLOT, THREADS = Sh::THREADS, COLS = Sh::COLS;
     constexpr int MAGS = Sh::mag_stride(ROWS);
+    constexpr bool PK = N == 8192; // the tail's per-frame arithmetic on packed pairs (vec_add / vec_scale / vec_fma, fft_device.cuh)
     static_assert(N == 16384 || N == 8192 || N == 4096 || N == 2048 || N == 1024,
                   "N = 16 M with M = 1024 (radix 16, 16, 4), 512 (radix 16, 16, 2), 256 (radix 16, 16), 128 (radix 16, 8) or 64 (radix 16, 4)");
     static_assert(COLS == 1 || (F == 2 && HOPQ == 0 && !RESIDENT), "M = 1024: one frame pair per tile, own samples, constants reloaded per column");
@@ -957,7 +957,7 @@ __global__ void __launch_bounds__(RdifShape<N, F>::THREADS, MINB) stft_bars_rdif
         }
         __syncthreads();
         // ================= bins -> bars, SG, outputs: every item carries the tile's F frames =================
-        rdif_segment_sums<F, MAGS>(t_seg, mags, segsum, p.nseg, t, THREADS);
+        rdif_segment_sums<F, MAGS, PK>(t_seg, mags, segsum, p.nseg, t, THREADS);
         __syncthreads();
         for (int b = t; b < B; b += THREADS) {
             const int a = t_bar0[b] & 0xffff, e = a + (t_bar0[b] >> 16); // the bar's range: first segment, count
@@ -966,18 +966,16 @@ __global__ void __launch_bounds__(RdifShape<N, F>::THREADS, MINB) stft_bars_rdif
             for (int k = a + 1; k < e; k++) {
                 float u[F];
                 FrameVec<F>::load(segsum + k * F, u);
-#pragma unroll
-                for (int f = 0; f < F; f++) acc[f] += u[f];
+                vec_add<F, PK>(acc, u);
             }
             const float inv = t_inv[b];
-#pragma unroll
-            for (int f = 0; f < F; f++) acc[f] *= inv;
+            vec_scale<F, PK>(acc, inv);
             FrameVec<F>::store(raw + b * F, acc);
         }
         __syncthreads();
         // band energy / bass first (16 lanes of warp 0; the magnitudes are still in place), then the heights
         if (t < 4 * F) rdif_emit_beat<F, SGW>(p, raw, t_sg, mags, MAGS, t, cur.ch, cur.first_frame(p, F));
-        rdif_emit_bars<F, SGW>(p, raw, t_sg, t, THREADS, cur.tic >= p.tic_emit_lo && cur.tic < p.tic_emit_hi, cur.o0, cur.first_frame(p, F));
+        rdif_emit_bars<F, SGW, PK>(p, raw, t_sg, t, THREADS, cur.tic >= p.tic_emit_lo && cur.tic < p.tic_emit_hi, cur.o0, cur.first_frame(p, F));
         // No barrier here: the next tile's pass A starts at once; the barrier that protects the aliased
         // buffers is the one inside (late_alias) or in front of (otherwise) its pass A.
     }

@@ -42,6 +42,15 @@ class StreamingSpectrum:
     def launch_count(self):
         return int(_capi.lib().fftl_stream_launch_count(self._h))
 
+    @property
+    def fused_tick_count(self):
+        """Pushes that ran as ONE kernel (n = 1024 / 2048, exact window move: csrc/stream_tick.cuh)."""
+        return int(_capi.lib().fftl_stream_fused_tick_count(self._h))
+
+    def set_tick_kernel(self, which):
+        """``TICK_AUTO`` (one kernel per tick where built) or ``TICK_THREE_LAUNCHES`` (window move, bars kernel, beat stage)."""
+        _capi.check(_capi.lib().fftl_stream_set_tick_kernel(self._h, which))
+
     def push(self, fresh, want_i32=True, out=None):
         """fresh: int16 numpy [streams, count]. Returns dict(bars [streams,B], bars_i32, beat [streams])."""
         fresh = np.ascontiguousarray(fresh, dtype=np.int16)

@@ -206,6 +206,13 @@ int  fftl_stream_push_device_f32(fftl_stream* s, const float* fresh_dev, int32_t
                                  int64_t sample_stride, float* bars_dev, int32_t* bars_i32_dev, fftl_beat* beat_dev,
                                  void* cuda_stream);
 int64_t fftl_stream_launch_count(const fftl_stream* s);
+/* How a push runs: AUTO = one kernel per tick where it is built (n = 1024 / 2048 with FFTL_MOVE_EXACT: window move,
+ * transform with 4 points per thread, bars and beat stage of two streams per CTA -- laid out for latency), else the
+ * three launches (window move, batched bars kernel, beat stage); THREE_LAUNCHES = always the latter (what the one-kernel
+ * tick is tested against).  fftl_stream_fused_tick_count: pushes that ran as one kernel.                          */
+enum { FFTL_TICK_AUTO = 0, FFTL_TICK_THREE_LAUNCHES = 1 };
+int  fftl_stream_set_tick_kernel(fftl_stream* s, int32_t which);
+int64_t fftl_stream_fused_tick_count(const fftl_stream* s);
 /* Render-side history (the reference's "3D mode" keeps the last ~96 bar frames on screen by feeding the
  * bitmap back, drawBar2D.cpp:405-426,670-680).  depth > 0 keeps the last `depth` float bar frames of every
  * stream on the device; fftl_stream_history_device copies them out oldest first as [streams][depth][bars]

@@ -207,6 +207,7 @@ def test_1024_stream_tick_against_the_oracle(oracle, lib):
             assert_bars_close(hb[spots], ref_h, "tick %d" % k)
             assert_int_heights(hi[spots], ref_i, ref_h, "tick %d" % k)
             series.append(bt[spots].copy())
+        assert ss.fused_tick_count == ticks and ss.launch_count == ticks   # the one-kernel tick (stream_tick.cuh) ran
     for q, s in enumerate(spots):
         one = np.array([series[k][q] for k in range(ticks)], dtype=series[0].dtype)
         assert_peaks_explained(oracle, oc, one, "stream %d" % s)

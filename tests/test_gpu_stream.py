@@ -34,16 +34,19 @@ def move_array_exact(dest, fresh):
     return np.concatenate([dest[add:], fresh])
 
 
-@pytest.mark.parametrize("mode", ["exact", "reference"])
-def test_streaming_ticks_match_oracle(oracle, lib, mode):
-    n, B, streams = 1024, 64, 7
+@pytest.mark.parametrize("mode,n,tick", [("exact", 1024, "one_kernel"), ("exact", 2048, "one_kernel"), ("exact", 1024, "three_launches"),
+                                         ("exact", 4096, "three_launches"), ("reference", 1024, "three_launches")])
+def test_streaming_ticks_match_oracle(oracle, lib, mode, n, tick):
+    """Every tick of every stream against the oracle, through both forms of a push: the one-kernel tick (stream_tick.cuh:
+    n = 1024 / 2048 with the exact window move) and the three launches (window move, batched bars kernel, beat stage)."""
+    B, streams = 64, 7
     cfg = lib.extended_config(n, 1024, B) if mode == "exact" else lib.reference_config(n, 1024, 100)
     B = cfg.bars
     oc = _ocfg(oracle, cfg)
     rng = np.random.default_rng(11)
-    counts = [1024, 512, 480, 1, 777, 1024, 300] + [int(c) for c in rng.integers(200, 1025, 40)]
+    counts = [n, 512, 480, 1, 777, n, 300] + [int(c) for c in rng.integers(200, n + 1, 40)]
     if mode == "exact":
-        counts[3] = 1500                         # more new samples than the window holds
+        counts[3] = n + 476                      # more new samples than the window holds
     total = sum(counts)
     src = oracle.synth_pcm(streams, total)
     win = np.zeros((streams, n), np.int16)
@@ -53,6 +56,8 @@ def test_streaming_ticks_match_oracle(oracle, lib, mode):
     got_beat = []
     pos = 0
     with lib.StreamingSpectrum(cfg, streams, lib.MOVE_EXACT if mode == "exact" else lib.MOVE_REFERENCE) as ss:
+        if tick == "three_launches":
+            ss.set_tick_kernel(lib.TICK_THREE_LAUNCHES)
         for k, c in enumerate(counts):
             fresh = src[:, pos:pos + c]
             pos += c
@@ -67,7 +72,8 @@ def test_streaming_ticks_match_oracle(oracle, lib, mode):
             got_w[:, k] = got["beat"]["w"]
             got_bass[:, k] = got["beat"]["bass"]
             got_beat.append(got["beat"].copy())
-        assert ss.launch_count == 3 * len(counts)
+        assert ss.launch_count == (1 if tick == "one_kernel" else 3) * len(counts)
+        assert ss.fused_tick_count == (len(counts) if tick == "one_kernel" else 0)
     # integer stages replayed by the oracle on the GPU's own (w, bass) series: bit exact
     # (peak index: equal, or explained as an integer-boundary flip; movement = N * timeDelta * index with this tick's count)
     n_dt = np.array([np.float32(n) * (np.float32(c) / np.float32(cfg.sample_rate)) for c in counts], np.float32)

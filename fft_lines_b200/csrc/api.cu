@@ -1110,7 +1110,7 @@ extern "C" int fftl_stream_push_device(fftl_stream* s, const int16_t* fresh, int
         count = c.n;
     }
     if (s->tick_kernel == FFTL_TICK_AUTO && s->move_mode == FFTL_MOVE_EXACT && (c.n == 1024 || c.n == 2048) &&
-        stream_tick_smem<2048>(c.bars, c.sg_half) <= 48 * 1024) {
+        stream_tick_smem<2048>(c.bars, c.sg_half) <= 28 * 1024) {
         StftParams p;
         memset(&p, 0, sizeof(p));
         p.window = h->d_window;

@@ -36,6 +36,17 @@ __device__ __forceinline__ float f64_to_f32(double x)
     return r;
 }
 
+// One bin of the carried transform: X[k] += delta * W256^(pos k), heightBuffer[k] = (int)|X[k]| (beatDetector.c:69-75)
+__device__ __forceinline__ void stream_carry_bin(const double delta, const double2 w, double2& x, const int kk, int* hrow, const int strict)
+{
+    x.x = fma(delta, w.x, x.x);
+    x.y = fma(delta, w.y, x.y);
+    const float mag = __fsqrt_rn(f64_to_f32(fma(x.x, x.x, x.y * x.y))); // correctly rounded: feeds an (int) cast
+    const int hv = trunc_i32(mag, strict);
+    hrow[kk] = hv;
+    if (kk >= FFTL_TEMPO_RING - FFTL_BEAT_SAMPLES && kk < FFTL_TEMPO_RING / 2) hrow[FFTL_TEMPO_RING - kk] = hv; // |X[256-k]| = |X[k]|: bins 129..160
+}
+
 struct StreamCarry {
     const int* aux_w;       // [streams] band energy of this tick
     const int* aux_bass;    // [streams] (int)|X[bass_bin]| of this tick
@@ -54,6 +65,87 @@ struct StreamCarry {
 
 constexpr int STREAM_CARRY_BINS = FFTL_TEMPO_RING / 2 + 1; // 129
 constexpr int STREAM_CARRY_HROW = FFTL_BEAT_SAMPLES + 4;   // heightBuffer[0..160] of one stream
+
+// Peak scan of the two height rows in s_h (beatDetector.c:78-103) by 16 consecutive lanes of one warp (tid = 0..15; 8 lanes
+// per stream; lanes 16..31 of that warp must not be inside a diverged call of this function): returns the tempo peak of
+// stream tid / 8, valid in lanes tid = 0 and tid = 8.
+__device__ __forceinline__ int stream_carry_peak(const int* s_h, const int tid)
+{
+    // same code shape as beat_post_kernel
+    const unsigned lane_id = threadIdx.x & 31u;
+    const unsigned MASK = 0xffffu << ((lane_id - (unsigned)tid) & 31u); // the 16 lanes this call runs on
+    const int si = tid >> 3, sub = tid & 7;
+    const int* h = s_h + si * STREAM_CARRY_HROW;
+    const int i0 = 20 * sub;
+    unsigned bits = 0;
+    int prev = (i0 == 0) ? 0 : h[i0 - 1];
+    int cur = h[i0];
+#pragma unroll
+    for (int qq = 0; qq < 20; qq++) {
+        int nxt = h[i0 + qq + 1];
+        int dold = (i0 + qq == 0) ? 0 : wrap_sub(cur, prev);
+        int dnew = wrap_sub(nxt, cur);
+        if (dold >= 0 && dnew <= 0) bits |= 1u << qq;
+        prev = cur;
+        cur = nxt;
+    }
+    int cnt = __popc(bits), incl = cnt;
+#pragma unroll
+    for (int o = 1; o < 8; o <<= 1) {
+        int n = __shfl_up_sync(MASK, incl, o, 8);
+        if (sub >= o) incl += n;
+    }
+    int rank = incl - cnt;
+    int best_val = 0, best_idx = -1;
+    int first = bits ? (i0 + __ffs(bits) - 1) : 1 << 30;
+    unsigned bb = bits;
+    while (bb) {
+        int qq = __ffs(bb) - 1;
+        bb &= bb - 1;
+        int i = i0 + qq;
+        int hv = h[i];
+        if (rank < 30 && i > 30 && hv > best_val) {
+            best_val = hv;
+            best_idx = i;
+        }
+        rank++;
+    }
+#pragma unroll
+    for (int o = 4; o > 0; o >>= 1) {
+        int ov = __shfl_xor_sync(MASK, best_val, o, 8);
+        int oi = __shfl_xor_sync(MASK, best_idx, o, 8);
+        int of = __shfl_xor_sync(MASK, first, o, 8);
+        bool take = (oi >= 0) && (best_idx < 0 || ov > best_val || (ov == best_val && oi < best_idx));
+        if (take) {
+            best_val = ov;
+            best_idx = oi;
+        }
+        first = of < first ? of : first;
+    }
+    return best_idx >= 0 ? best_idx : (first < (1 << 30) ? first : 0);
+}
+
+// AddBeatSample (beatDetector.c:30-44) on stream ss's own ring and the tick's beat record: w / bass = this tick's band energy
+// and bass value, w_old = the slot of the beat ring that is overwritten, w_sum = the ring's running sum.  One thread.
+__device__ __forceinline__ void stream_carry_record(const StreamCarry& q, const int ss, const int pos160, const int peak, const int w, const int bass,
+                                                    const int w_old, const int w_sum)
+{
+    const int sum = wrap_sub(wrap_add(w_sum, w), w_old);
+    q.w_ring[(long long)ss * FFTL_BEAT_SAMPLES + pos160] = w;
+    q.w_sum[ss] = sum;
+    const int thr = sum / FFTL_BEAT_SAMPLES;
+    const float qv = __fdiv_rn((float)w, (float)thr);
+    fftl_beat rec;
+    rec.w = w;
+    rec.thr = thr;
+    rec.beat_value = trunc_i32(__fmul_rn(qv, 128.0f), 1);
+    rec.flag = (thr > 0 && w > thr) ? 1 : 0;
+    rec.bass = bass;
+    rec.peak_index = peak;
+    rec.movement_per_sec = __fmul_rn(q.n_times_dt, (float)peak);
+    rec.reserved = 0;
+    q.out[ss] = rec;
+}
 
 // Streams s0 and s0 + 1 by THREADS threads (a multiple of 64; tid = 0..THREADS-1): THREADS/2 threads per stream, one or
 // more bins each (the function was also run with 64 threads as an epilogue of the bars kernel: DESIGN.md section 4.4).  s_h: [2][STREAM_CARRY_HROW] ints of shared memory.  Contains two CTA barriers: every thread of the
@@ -77,89 +169,17 @@ __device__ __forceinline__ void stream_carry_pair(const StreamCarry& q, const lo
         for (int kk = lane; kk < STREAM_CARRY_BINS; kk += LPS) {
             const double2 w = __ldg(q.tw256d + ((pos256 * kk) & (FFTL_TEMPO_RING - 1)));
             double2 x = xs[kk];
-            x.x = fma(delta, w.x, x.x);
-            x.y = fma(delta, w.y, x.y);
+            stream_carry_bin(delta, w, x, kk, hrow, q.strict);
             xs[kk] = x;
-            const float mag = __fsqrt_rn(f64_to_f32(fma(x.x, x.x, x.y * x.y))); // correctly rounded: feeds an (int) cast
-            const int hv = trunc_i32(mag, q.strict);
-            hrow[kk] = hv;
-            if (kk >= FFTL_TEMPO_RING - FFTL_BEAT_SAMPLES && kk < FFTL_TEMPO_RING / 2) hrow[FFTL_TEMPO_RING - kk] = hv; // |X[256-k]| = |X[k]|: bins 129..160
         }
     }
     __syncthreads();
     if (valid && lane == 0) ring[pos256] = nv; // every thread of the stream has read the old value
     if (tid < 16) {
-        // peak scan, 8 lanes per stream (same code shape as beat_post_kernel)
-        const int si = tid >> 3, sub = tid & 7;
-        const int ss = s0 + si;
-        const int* h = s_h + si * STREAM_CARRY_HROW;
-        const int i0 = 20 * sub;
-        unsigned bits = 0;
-        int prev = (i0 == 0) ? 0 : h[i0 - 1];
-        int cur = h[i0];
-#pragma unroll
-        for (int qq = 0; qq < 20; qq++) {
-            int nxt = h[i0 + qq + 1];
-            int dold = (i0 + qq == 0) ? 0 : wrap_sub(cur, prev);
-            int dnew = wrap_sub(nxt, cur);
-            if (dold >= 0 && dnew <= 0) bits |= 1u << qq;
-            prev = cur;
-            cur = nxt;
-        }
-        int cnt = __popc(bits), incl = cnt;
-#pragma unroll
-        for (int o = 1; o < 8; o <<= 1) {
-            int n = __shfl_up_sync(0xffffu, incl, o, 8);
-            if (sub >= o) incl += n;
-        }
-        int rank = incl - cnt;
-        int best_val = 0, best_idx = -1;
-        int first = bits ? (i0 + __ffs(bits) - 1) : 1 << 30;
-        unsigned bb = bits;
-        while (bb) {
-            int qq = __ffs(bb) - 1;
-            bb &= bb - 1;
-            int i = i0 + qq;
-            int hv = h[i];
-            if (rank < 30 && i > 30 && hv > best_val) {
-                best_val = hv;
-                best_idx = i;
-            }
-            rank++;
-        }
-#pragma unroll
-        for (int o = 4; o > 0; o >>= 1) {
-            int ov = __shfl_xor_sync(0xffffu, best_val, o, 8);
-            int oi = __shfl_xor_sync(0xffffu, best_idx, o, 8);
-            int of = __shfl_xor_sync(0xffffu, first, o, 8);
-            bool take = (oi >= 0) && (best_idx < 0 || ov > best_val || (ov == best_val && oi < best_idx));
-            if (take) {
-                best_val = ov;
-                best_idx = oi;
-            }
-            first = of < first ? of : first;
-        }
-        if (sub == 0 && ss < q.streams) {
-            const int peak = best_idx >= 0 ? best_idx : (first < (1 << 30) ? first : 0);
-            // AddBeatSample (beatDetector.c:30-44) on the stream's own ring
-            const int w = q.aux_w[ss];
-            int* wr = q.w_ring + (long long)ss * FFTL_BEAT_SAMPLES;
-            int sum = wrap_sub(wrap_add(q.w_sum[ss], w), wr[pos160]);
-            wr[pos160] = w;
-            q.w_sum[ss] = sum;
-            const int thr = sum / FFTL_BEAT_SAMPLES;
-            const float qv = __fdiv_rn((float)w, (float)thr);
-            fftl_beat rec;
-            rec.w = w;
-            rec.thr = thr;
-            rec.beat_value = trunc_i32(__fmul_rn(qv, 128.0f), 1);
-            rec.flag = (thr > 0 && w > thr) ? 1 : 0;
-            rec.bass = q.aux_bass[ss];
-            rec.peak_index = peak;
-            rec.movement_per_sec = __fmul_rn(q.n_times_dt, (float)peak);
-            rec.reserved = 0;
-            q.out[ss] = rec;
-        }
+        const int peak = stream_carry_peak(s_h, tid);
+        const int ss = s0 + (tid >> 3);
+        if ((tid & 7) == 0 && ss < q.streams)
+            stream_carry_record(q, ss, pos160, peak, q.aux_w[ss], q.aux_bass[ss], q.w_ring[(long long)ss * FFTL_BEAT_SAMPLES + pos160], q.w_sum[ss]);
     }
     __syncthreads(); // s_h may be reused by the caller
 }

@@ -11,8 +11,10 @@
 //     through shared memory (five at N = 1024), every thread's dependent chain a quarter of the 16-point form;
 //   * untangle + magnitudes (fft_lines.c:202), log bars by up to 8 lanes per bar with a shuffle reduction, Savitzky-Golay,
 //     zoom, (int) heights, band energy and bass bin (fft_lines.c:195-208, :281; beatDetector.c:53);
-//   * AddBeatSample / BassBeatDetector on the streams' rings with the carried tempo transform (stream_carry.cuh), the
-//     last CTA advancing the device-resident tick counter.
+//   * AddBeatSample / BassBeatDetector on the streams' rings with the carried tempo transform (stream_carry.cuh): the ring
+//     state is fetched at the start of the kernel, the bins are updated between the untangling and the bars, the peak scan
+//     runs on the last warp beside the Savitzky-Golay step; the CTA that arrives last at the device-resident tick counter
+//     advances it (the arrival itself is made at the start, so its round trip is off the tail).
 // Used for N = 1024 and 2048 with the exact window move; every other case keeps the three launches.
 #pragma once
 #include "kernels.cuh"
@@ -75,10 +77,21 @@ __device__ __forceinline__ void tick_fft_rest(float2* v, float2* s, const float2
     }
 }
 
-template <int N>
-__global__ void __launch_bounds__(N / 4) stream_tick_kernel(const StftParams p, const StreamTickParams k, const StreamCarry q)
+// 16 bytes global -> shared memory without a register in between (LDGSTS); completion: cp.async.wait_all by the same thread
+__device__ __forceinline__ void cp_async16(void* smem_dst, const void* gmem_src)
 {
-    constexpr int G = N / 4; // threads per CTA = per stream pair
+    asm volatile("cp.async.ca.shared.global [%0], [%1], 16;" ::"r"((unsigned)__cvta_generic_to_shared(smem_dst)), "l"(gmem_src) : "memory");
+}
+
+__device__ __forceinline__ void cp_async4(void* smem_dst, const void* gmem_src)
+{
+    asm volatile("cp.async.ca.shared.global [%0], [%1], 4;" ::"r"((unsigned)__cvta_generic_to_shared(smem_dst)), "l"(gmem_src) : "memory");
+}
+
+template <int N>
+__global__ void __launch_bounds__(N / 4, 4096 / N) stream_tick_kernel(const StftParams p, const StreamTickParams k, const StreamCarry q)
+{
+    constexpr int G = N / 4; // threads per CTA = per stream pair; 64 registers: 1024 streams of 1024 points are one wave (four CTAs per SM)
     extern __shared__ float2 smem[];
     __shared__ int s_h[2 * STREAM_CARRY_HROW];
     __shared__ int beat_h[8];
@@ -88,10 +101,13 @@ __global__ void __launch_bounds__(N / 4) stream_tick_kernel(const StftParams p, 
     float* t_sg = raw + 2 * B;                                    // [(2w+1)^2] Savitzky-Golay matrix
     auto sync = [] { __syncthreads(); };
     const int g = threadIdx.x;
-    const long long tick = q.state->tick;
     const int sa = 2 * blockIdx.x;
     const bool has_b = sa + 1 < k.streams;
-    // everything that depends on the thread only is asked for up front: twiddles, the first bar's bin range, the SG matrix
+    // The tick counter is read exactly once (volatile): the CTA that arrives last at `done` advances it (stream_finish),
+    // and a CTA may arrive as soon as it has its copy -- the arrival carries a (zero) term of the loaded value, so the
+    // atomic cannot be issued before the load has returned.  The round trip of the atomic is then off the kernel's tail.
+    const long long tick = *reinterpret_cast<const volatile long long*>(&q.state->tick);
+    // everything that depends on the thread only is asked for first: twiddles, the first bar's bin range, the SG matrix, the window column
     float2 twv[tick_twiddle_count<N>()];
     tick_twiddles<N, G, 4>(twv, p.tw, g);
     const int L = B * 8 <= G ? 8 : B * 4 <= G ? 4 : B * 2 <= G ? 2 : 1; // lanes per bar in the bins -> bars step
@@ -105,7 +121,10 @@ __global__ void __launch_bounds__(N / 4) stream_tick_kernel(const StftParams p, 
     }
     const int w = p.sg_half, m = 2 * w + 1;
     if (w > 0)
-        for (int i = g; i < m * m; i += G) t_sg[i] = __ldg(p.sg + i);
+        for (int i = g; i < m * m; i += G) cp_async4(t_sg + i, p.sg + i);
+    float wn[4];
+#pragma unroll
+    for (int r = 0; r < 4; r++) wn[r] = p.window ? __ldg(p.window + g + r * G) : 1.0f;
 
     // ---- MoveArray, in place (this CTA is the only one that touches its two windows)
     int16_t* wa = k.window + (long long)sa * N;
@@ -120,6 +139,44 @@ __global__ void __launch_bounds__(N / 4) stream_tick_kernel(const StftParams p, 
         xa[r] = i < keep ? wa[i + k.count] : __ldg(fa + (i - keep));
         xb[r] = has_b ? (i < keep ? wb[i + k.count] : __ldg(fb + (i - keep))) : (int16_t)0;
     }
+    // ---- everything that depends on the tick, behind the loads that do not
+    unsigned arrived = 0;
+    if (q.finish && g == 0) arrived = atomicAdd(&q.state->done, 1u + (unsigned)((unsigned long long)tick >> 63));
+    // beat state of this tick, asked for now and used behind the transform: the tempo-ring slot that is overwritten, the
+    // carried transform's bins of this thread and their twiddles, the beat ring's slot and sum (stream_carry.cuh)
+    constexpr int LPS = G / 2; // lanes per stream in the beat stage
+    const int half = g / LPS, lane = g - half * LPS;
+    const int sc = sa + half;
+    const bool valid = sc < k.streams;
+    const int pos256 = (int)(tick % FFTL_TEMPO_RING), pos160 = (int)(tick % FFTL_BEAT_SAMPLES);
+    int* ring = q.tempo_ring + (long long)sc * FFTL_TEMPO_RING;
+    double2* xs = q.x + (long long)sc * STREAM_CARRY_BINS;
+    // one bin per thread, the bins beyond LPS (bin 128 at N = 1024) on the first lanes: copied global -> shared memory
+    // asynchronously (cp.async: no register is held across the transform), read back by the same thread
+    constexpr int EX = STREAM_CARRY_BINS > LPS ? STREAM_CARRY_BINS - LPS : 0;
+    static_assert(EX <= LPS, "at most two bins per thread");
+    __shared__ double2 s_cx[G + 2 * EX], s_cw[G + 2 * EX];
+    int ring_old = 0;
+    if (valid) {
+        ring_old = ring[pos256];
+        if (lane < STREAM_CARRY_BINS) {
+            cp_async16(s_cx + g, xs + lane);
+            cp_async16(s_cw + g, q.tw256d + ((pos256 * lane) & (FFTL_TEMPO_RING - 1)));
+        }
+        if (lane < EX) {
+            cp_async16(s_cx + G + half * EX + lane, xs + LPS + lane);
+            cp_async16(s_cw + G + half * EX + lane, q.tw256d + ((pos256 * (LPS + lane)) & (FFTL_TEMPO_RING - 1)));
+        }
+    }
+    // the peak scan and the beat record run on the first 16 lanes of the CTA's last warp (lanes 0 and 8 write the records)
+    const int st = g - (G - 32);
+    const int srec = sa + (st >> 3);
+    const bool rec_lane = st >= 0 && st < 16 && (st & 7) == 0 && srec < k.streams;
+    int w_old = 0, w_sum = 0;
+    if (rec_lane) {
+        w_old = q.w_ring[(long long)srec * FFTL_BEAT_SAMPLES + pos160];
+        w_sum = q.w_sum[srec];
+    }
     __syncthreads();
     float2 v[4];
 #pragma unroll
@@ -129,9 +186,8 @@ __global__ void __launch_bounds__(N / 4) stream_tick_kernel(const StftParams p, 
         if (has_b) wb[i] = xb[r];
         float a = (float)xa[r], b = (float)xb[r];
         if (p.window) {
-            const float wn = __ldg(p.window + i);
-            a *= wn;
-            b *= wn;
+            a *= wn[r];
+            b *= wn[r];
         }
         v[r] = make_float2(a, b); // z[i] = window_a[i] + i*window_b[i]
     }
@@ -146,6 +202,27 @@ __global__ void __launch_bounds__(N / 4) stream_tick_kernel(const StftParams p, 
         s[pad_index(kk)] = make_float2(0.5f * sqrtf(fmaf(ar, ar, ai * ai)), 0.5f * sqrtf(fmaf(br, br, bi * bi)));
     }
     __syncthreads();
+
+    // ---- tempo ring: bass = (int)|X[bass_bin]| (beatDetector.c:53) enters the carried transform, heightBuffer into s_h
+    int bass = 0;
+    asm volatile("cp.async.wait_all;" ::: "memory"); // this thread's copies (the SG matrix becomes visible to the others at the next barrier)
+    if (valid) {
+        const float2 mb = s[pad_index(p.bass_bin)];
+        bass = trunc_i32(half == 0 ? mb.x : mb.y, p.strict);
+        const double delta = (double)(float)bass - (double)(float)ring_old; // the reference transforms the ring as floats (beatDetector.c:61-65)
+        int* hrow = s_h + half * STREAM_CARRY_HROW;
+        if (lane < STREAM_CARRY_BINS) {
+            double2 x = s_cx[g];
+            stream_carry_bin(delta, s_cw[g], x, lane, hrow, q.strict);
+            xs[lane] = x;
+        }
+        if (lane < EX) {
+            double2 x = s_cx[G + half * EX + lane];
+            stream_carry_bin(delta, s_cw[G + half * EX + lane], x, LPS + lane, hrow, q.strict);
+            xs[LPS + lane] = x;
+        }
+        if (lane == 0) ring[pos256] = bass;
+    }
 
     // ---- bins -> bars: mean of the magnitudes over [lo, hi), L lanes per bar (L = 8, 4, 2 or 1: as many as the CTA has)
     for (int b0 = 0; b0 < B; b0 += per) {
@@ -218,21 +295,25 @@ __global__ void __launch_bounds__(N / 4) stream_tick_kernel(const StftParams p, 
                 beat_h[4 + t] = ib;
             }
     }
+    // meanwhile on the last warp: the peak scan of the two height rows (written before the previous barrier)
+    int peak = 0, bass_rec = 0;
+    if (st >= 0 && st < 16) {
+        peak = stream_carry_peak(s_h, st);
+        const float2 mb = s[pad_index(p.bass_bin)];
+        bass_rec = trunc_i32((st >> 3) == 0 ? mb.x : mb.y, p.strict);
+    }
     __syncthreads();
 
-    // ---- band energy w (fft_lines.c:281) and bass bin (beatDetector.c:53) of the two streams
-    if (g < 2 && (g == 0 || has_b)) {
-        const int* h4 = beat_h + 4 * g;
-        const int sum = wrap_add(wrap_add(h4[0], h4[1]), wrap_add(h4[2], h4[3]));
-        const float2 mb = s[pad_index(p.bass_bin)];
-        p.aux_w[sa + g] = sum / 4;
-        p.aux_bass[sa + g] = trunc_i32(g == 0 ? mb.x : mb.y, p.strict);
+    // ---- band energy w (fft_lines.c:281), AddBeatSample and the beat record: lanes 0 and 8 of the last warp
+    if (rec_lane) {
+        const int* h4 = beat_h + 4 * (st >> 3);
+        const int wsum4 = wrap_add(wrap_add(h4[0], h4[1]), wrap_add(h4[2], h4[3]));
+        stream_carry_record(q, srec, pos160, peak, wsum4 / 4, bass_rec, w_old, w_sum);
     }
-    __syncthreads(); // the beat stage reads them back (same CTA: the barrier orders the global writes)
-
-    // ---- AddBeatSample + BassBeatDetector with the carried tempo transform
-    stream_carry_pair<G>(q, tick, sa, s_h, g);
-    if (q.finish) stream_finish(q.state);
+    if (q.finish && g == 0 && arrived == gridDim.x - 1) { // every CTA has its copy of the tick: this one arrived last
+        q.state->done = 0;
+        q.state->tick = tick + 1;
+    }
 }
 
 template <int N> static size_t stream_tick_smem(int bars, int sg_half)

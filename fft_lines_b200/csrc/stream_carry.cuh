@@ -66,22 +66,20 @@ struct StreamCarry {
 constexpr int STREAM_CARRY_BINS = FFTL_TEMPO_RING / 2 + 1; // 129
 constexpr int STREAM_CARRY_HROW = FFTL_BEAT_SAMPLES + 4;   // heightBuffer[0..160] of one stream
 
-// Peak scan of the two height rows in s_h (beatDetector.c:78-103) by 16 consecutive lanes of one warp (tid = 0..15; 8 lanes
-// per stream; lanes 16..31 of that warp must not be inside a diverged call of this function): returns the tempo peak of
-// stream tid / 8, valid in lanes tid = 0 and tid = 8.
-__device__ __forceinline__ int stream_carry_peak(const int* s_h, const int tid)
+// Peak scan of one stream's height row h[0..160] (beatDetector.c:78-103) by LANES (8, 16 or 32) consecutive lanes of one
+// warp, 160 / LANES bins each (sub = 0..LANES-1; mask = those lanes, or all the lanes of the warp that make this call
+// together): returns the tempo peak, valid in the lane with sub = 0.
+template <int LANES> __device__ __forceinline__ int stream_carry_peak(const int* h, const int sub, const unsigned mask)
 {
     // same code shape as beat_post_kernel
-    const unsigned lane_id = threadIdx.x & 31u;
-    const unsigned MASK = 0xffffu << ((lane_id - (unsigned)tid) & 31u); // the 16 lanes this call runs on
-    const int si = tid >> 3, sub = tid & 7;
-    const int* h = s_h + si * STREAM_CARRY_HROW;
-    const int i0 = 20 * sub;
+    constexpr int PER = FFTL_BEAT_SAMPLES / LANES;
+    static_assert(PER * LANES == FFTL_BEAT_SAMPLES && LANES <= 32, "160 bins split evenly");
+    const int i0 = PER * sub;
     unsigned bits = 0;
     int prev = (i0 == 0) ? 0 : h[i0 - 1];
     int cur = h[i0];
 #pragma unroll
-    for (int qq = 0; qq < 20; qq++) {
+    for (int qq = 0; qq < PER; qq++) {
         int nxt = h[i0 + qq + 1];
         int dold = (i0 + qq == 0) ? 0 : wrap_sub(cur, prev);
         int dnew = wrap_sub(nxt, cur);
@@ -91,8 +89,8 @@ __device__ __forceinline__ int stream_carry_peak(const int* s_h, const int tid)
     }
     int cnt = __popc(bits), incl = cnt;
 #pragma unroll
-    for (int o = 1; o < 8; o <<= 1) {
-        int n = __shfl_up_sync(MASK, incl, o, 8);
+    for (int o = 1; o < LANES; o <<= 1) {
+        int n = __shfl_up_sync(mask, incl, o, LANES);
         if (sub >= o) incl += n;
     }
     int rank = incl - cnt;
@@ -111,10 +109,10 @@ __device__ __forceinline__ int stream_carry_peak(const int* s_h, const int tid)
         rank++;
     }
 #pragma unroll
-    for (int o = 4; o > 0; o >>= 1) {
-        int ov = __shfl_xor_sync(MASK, best_val, o, 8);
-        int oi = __shfl_xor_sync(MASK, best_idx, o, 8);
-        int of = __shfl_xor_sync(MASK, first, o, 8);
+    for (int o = LANES / 2; o > 0; o >>= 1) {
+        int ov = __shfl_xor_sync(mask, best_val, o, LANES);
+        int oi = __shfl_xor_sync(mask, best_idx, o, LANES);
+        int of = __shfl_xor_sync(mask, first, o, LANES);
         bool take = (oi >= 0) && (best_idx < 0 || ov > best_val || (ov == best_val && oi < best_idx));
         if (take) {
             best_val = ov;
@@ -176,7 +174,7 @@ __device__ __forceinline__ void stream_carry_pair(const StreamCarry& q, const lo
     __syncthreads();
     if (valid && lane == 0) ring[pos256] = nv; // every thread of the stream has read the old value
     if (tid < 16) {
-        const int peak = stream_carry_peak(s_h, tid);
+        const int peak = stream_carry_peak<8>(s_h + (tid >> 3) * STREAM_CARRY_HROW, tid & 7, 0xffffu << ((threadIdx.x - (unsigned)tid) & 31u));
         const int ss = s0 + (tid >> 3);
         if ((tid & 7) == 0 && ss < q.streams)
             stream_carry_record(q, ss, pos160, peak, q.aux_w[ss], q.aux_bass[ss], q.w_ring[(long long)ss * FFTL_BEAT_SAMPLES + pos160], q.w_sum[ss]);

@@ -103,10 +103,6 @@ __global__ void __launch_bounds__(N / 4, 4096 / N) stream_tick_kernel(const Stft
     const int g = threadIdx.x;
     const int sa = 2 * blockIdx.x;
     const bool has_b = sa + 1 < k.streams;
-    // The tick counter is read exactly once (volatile): the CTA that arrives last at `done` advances it (stream_finish),
-    // and a CTA may arrive as soon as it has its copy -- the arrival carries a (zero) term of the loaded value, so the
-    // atomic cannot be issued before the load has returned.  The round trip of the atomic is then off the kernel's tail.
-    const long long tick = *reinterpret_cast<const volatile long long*>(&q.state->tick);
     // everything that depends on the thread only is asked for first: twiddles, the first bar's bin range, the SG matrix, the window column
     float2 twv[tick_twiddle_count<N>()];
     tick_twiddles<N, G, 4>(twv, p.tw, g);
@@ -139,7 +135,14 @@ __global__ void __launch_bounds__(N / 4, 4096 / N) stream_tick_kernel(const Stft
         xa[r] = i < keep ? wa[i + k.count] : __ldg(fa + (i - keep));
         xb[r] = has_b ? (i < keep ? wb[i + k.count] : __ldg(fb + (i - keep))) : (int16_t)0;
     }
-    // ---- everything that depends on the tick, behind the loads that do not
+    // ---- everything that depends on the tick, behind the loads that do not (the asm's memory clobber keeps them in front)
+    // The tick counter is read exactly once, through the L1 (one L2 request per SM instead of one per warp on one L2
+    // line; the counter changes only once every CTA has its copy, and the next kernel starts with a clean L1).  The CTA
+    // that arrives last at `done` advances it (stream_finish), and a CTA may arrive as soon as it has its copy: the
+    // arrival carries a (zero) term of the loaded value, so the atomic cannot be issued before the load has returned,
+    // and its round trip is off the kernel's tail.
+    long long tick;
+    asm volatile("ld.global.nc.s64 %0, [%1];" : "=l"(tick) : "l"(&q.state->tick) : "memory");
     unsigned arrived = 0;
     if (q.finish && g == 0) arrived = atomicAdd(&q.state->done, 1u + (unsigned)((unsigned long long)tick >> 63));
     // beat state of this tick, asked for now and used behind the transform: the tempo-ring slot that is overwritten, the
@@ -168,10 +171,11 @@ __global__ void __launch_bounds__(N / 4, 4096 / N) stream_tick_kernel(const Stft
             cp_async16(s_cw + G + half * EX + lane, q.tw256d + ((pos256 * (LPS + lane)) & (FFTL_TEMPO_RING - 1)));
         }
     }
-    // the peak scan and the beat record run on the first 16 lanes of the CTA's last warp (lanes 0 and 8 write the records)
-    const int st = g - (G - 32);
-    const int srec = sa + (st >> 3);
-    const bool rec_lane = st >= 0 && st < 16 && (st & 7) == 0 && srec < k.streams;
+    // the peak scan of stream a runs on the CTA's last warp but one, that of stream b on the last warp (32 lanes, 5 bins
+    // each); lane 0 of either writes the stream's beat record
+    const int si = (g >> 5) - (G / 32 - 2);
+    const int srec = sa + si;
+    const bool rec_lane = si >= 0 && (g & 31) == 0 && srec < k.streams;
     int w_old = 0, w_sum = 0;
     if (rec_lane) {
         w_old = q.w_ring[(long long)srec * FFTL_BEAT_SAMPLES + pos160];
@@ -295,18 +299,18 @@ __global__ void __launch_bounds__(N / 4, 4096 / N) stream_tick_kernel(const Stft
                 beat_h[4 + t] = ib;
             }
     }
-    // meanwhile on the last warp: the peak scan of the two height rows (written before the previous barrier)
+    // meanwhile on the last two warps: the peak scan of the two height rows (written before the previous barrier)
     int peak = 0, bass_rec = 0;
-    if (st >= 0 && st < 16) {
-        peak = stream_carry_peak(s_h, st);
+    if (si >= 0) {
+        peak = stream_carry_peak<32>(s_h + si * STREAM_CARRY_HROW, g & 31, 0xffffffffu);
         const float2 mb = s[pad_index(p.bass_bin)];
-        bass_rec = trunc_i32((st >> 3) == 0 ? mb.x : mb.y, p.strict);
+        bass_rec = trunc_i32(si == 0 ? mb.x : mb.y, p.strict);
     }
     __syncthreads();
 
-    // ---- band energy w (fft_lines.c:281), AddBeatSample and the beat record: lanes 0 and 8 of the last warp
+    // ---- band energy w (fft_lines.c:281), AddBeatSample and the beat record: lane 0 of the last two warps
     if (rec_lane) {
-        const int* h4 = beat_h + 4 * (st >> 3);
+        const int* h4 = beat_h + 4 * si;
         const int wsum4 = wrap_add(wrap_add(h4[0], h4[1]), wrap_add(h4[2], h4[3]));
         stream_carry_record(q, srec, pos160, peak, wsum4 / 4, bass_rec, w_old, w_sum);
     }

@@ -34,3 +34,24 @@ for name, which in (("one kernel per tick", F.TICK_AUTO), ("three launches per t
                 e1.record(st)
                 st.synchronize()
                 print("%s: %.2f us per tick (device, graph of %d tick(s) replayed back to back)" % (name, e0.elapsed_time(e1) * 1e3 / (1000 // TICKS * TICKS), TICKS))
+
+# the floor of this way of measuring: a graph of one (or eight) empty-ish kernel(s) replayed back to back
+one = torch.zeros(1, device=dev)
+st = torch.cuda.Stream()
+with torch.cuda.stream(st):
+    for TICKS in (1, 8):
+        one.add_(1.0)
+        st.synchronize()
+        g = torch.cuda.CUDAGraph()
+        with torch.cuda.graph(g, stream=st):
+            for _ in range(TICKS):
+                one.add_(1.0)
+        for _ in range(50):
+            g.replay()
+        e0, e1 = torch.cuda.Event(enable_timing=True), torch.cuda.Event(enable_timing=True)
+        e0.record(st)
+        for _ in range(1000 // TICKS):
+            g.replay()
+        e1.record(st)
+        st.synchronize()
+        print("one-element kernel: %.2f us per launch (graph of %d replayed back to back)" % (e0.elapsed_time(e1) * 1e3 / (1000 // TICKS * TICKS), TICKS))

@@ -369,6 +369,19 @@ def latency_leg(F, dev):
             e1.record(st)
             st.synchronize()
             dev_us = e0.elapsed_time(e1) * 1e3 / 500
+            # eight ticks per graph: the graph-launch gap (about 2 us between replays) is spread over eight ticks
+            g8 = torch.cuda.CUDAGraph()
+            with torch.cuda.graph(g8, stream=st):
+                for _ in range(8):
+                    ss.push_device(fresh, bars, None, beat, stream=st)
+            for _ in range(20):
+                g8.replay()
+            e0.record(st)
+            for _ in range(100):
+                g8.replay()
+            e1.record(st)
+            st.synchronize()
+            dev_us8 = e0.elapsed_time(e1) * 1e3 / 800
         h_fresh = F.PinnedArray((STREAMS, COUNT), np.int16)
         h_fresh.array[:] = fresh.cpu().numpy()
         hb, hbt = F.PinnedArray((STREAMS, B), np.float32), F.PinnedArray((STREAMS,), F.BEAT_DTYPE)
@@ -384,7 +397,8 @@ def latency_leg(F, dev):
         h_fresh.free(); hb.free(); hbt.free()
     return {"workload": "c3: 1024 concurrent mono streams, 1024-pt Hann, 64 log bars + SG + beat, one tick (512 new samples per stream) per batch",
             "frames_per_batch": STREAMS, "kernels_per_tick": int(per_tick),
-            "device_us_per_batch": dev_us, "frames_per_s_device": STREAMS / dev_us * 1e6,
+            "device_us_per_batch": dev_us, "device_us_per_batch_8_ticks_per_graph": dev_us8, "frames_per_s_device": STREAMS / dev_us * 1e6,
+            "tick_kernel": "stream_tick_kernel<1024> (one kernel per tick: csrc/stream_tick.cuh)" if per_tick == 1 else "window move + bars kernel + beat stage",
             "graph_replay_plus_sync": pct(lat_graph), "host_buffer_call": pct(lat_host),
             "note": "device = CUDA-graph replays back to back (events); graph_replay_plus_sync = one replay + stream sync seen "
                     "from the host; host_buffer_call = fftl_stream_push with pinned host buffers (H2D + tick + D2H + sync)"}

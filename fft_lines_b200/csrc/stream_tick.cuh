@@ -103,25 +103,6 @@ __global__ void __launch_bounds__(N / 4, 4096 / N) stream_tick_kernel(const Stft
     const int g = threadIdx.x;
     const int sa = 2 * blockIdx.x;
     const bool has_b = sa + 1 < k.streams;
-    // everything that depends on the thread only is asked for first: twiddles, the first bar's bin range, the SG matrix, the window column
-    float2 twv[tick_twiddle_count<N>()];
-    tick_twiddles<N, G, 4>(twv, p.tw, g);
-    const int L = B * 8 <= G ? 8 : B * 4 <= G ? 4 : B * 2 <= G ? 2 : 1; // lanes per bar in the bins -> bars step
-    const int sub = g & (L - 1), per = G / L;
-    int l0 = 0, h0 = 0;
-    float inv0 = 0.0f;
-    if (g / L < B) {
-        l0 = __ldg(p.lo + g / L);
-        h0 = __ldg(p.hi + g / L);
-        inv0 = __ldg(p.bar_inv + g / L);
-    }
-    const int w = p.sg_half, m = 2 * w + 1;
-    if (w > 0)
-        for (int i = g; i < m * m; i += G) cp_async4(t_sg + i, p.sg + i);
-    float wn[4];
-#pragma unroll
-    for (int r = 0; r < 4; r++) wn[r] = p.window ? __ldg(p.window + g + r * G) : 1.0f;
-
     // ---- MoveArray, in place (this CTA is the only one that touches its two windows)
     int16_t* wa = k.window + (long long)sa * N;
     int16_t* wb = wa + N;
@@ -135,6 +116,26 @@ __global__ void __launch_bounds__(N / 4, 4096 / N) stream_tick_kernel(const Stft
         xa[r] = i < keep ? wa[i + k.count] : __ldg(fa + (i - keep));
         xb[r] = has_b ? (i < keep ? wb[i + k.count] : __ldg(fb + (i - keep))) : (int16_t)0;
     }
+    // everything that depends on the thread only: twiddles, the first bar's bin range, the window column, the SG matrix
+    float2 twv[tick_twiddle_count<N>()];
+    tick_twiddles<N, G, 4>(twv, p.tw, g);
+    const int L = B * 8 <= G ? 8 : B * 4 <= G ? 4 : B * 2 <= G ? 2 : 1; // lanes per bar in the bins -> bars step
+    const int sub = g & (L - 1), per = G / L;
+    int l0 = 0, h0 = 0;
+    float inv0 = 0.0f;
+    if (g / L < B) {
+        l0 = __ldg(p.lo + g / L);
+        h0 = __ldg(p.hi + g / L);
+        inv0 = __ldg(p.bar_inv + g / L);
+    }
+    float wn[4];
+#pragma unroll
+    for (int r = 0; r < 4; r++) wn[r] = p.window ? __ldg(p.window + g + r * G) : 1.0f;
+
+    // (the loop's branches end the first basic block: everything above has its parameter reads hoisted to the kernel's top)
+    const int w = p.sg_half, m = 2 * w + 1;
+    if (w > 0)
+        for (int i = g; i < m * m; i += G) cp_async4(t_sg + i, p.sg + i);
     // ---- everything that depends on the tick, behind the loads that do not (the asm's memory clobber keeps them in front)
     // The tick counter is read exactly once, through the L1 (one L2 request per SM instead of one per warp on one L2
     // line; the counter changes only once every CTA has its copy, and the next kernel starts with a clean L1).  The CTA

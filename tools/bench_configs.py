@@ -110,7 +110,7 @@ out.append({"config": "c3: 1024 concurrent mono streams, 1024-pt Hann, 64 log ba
             "launch_sync_python": pct(lat_plain), "cuda_graph_replay_sync_python": pct(lat_graph),
             "c_abi_host_buffers_pinned": pct(lat_host), "frames_per_s_device": STREAMS / dev_us * 1e6,
             "h2d_bytes_per_batch": STREAMS * COUNT * 2, "d2h_bytes_per_batch": STREAMS * 64 * 4 + STREAMS * 32,
-            "note": "latency bound: 1024 frames are ~1 us of work at the roofline; 3 launches per tick: stream_slide_vec, stft_bars_kernel<1024>, stream_beat (its last CTA advances the tick)"})
+            "note": "latency bound: 1024 frames are ~1 us of work at the roofline; one kernel per tick (stream_tick_kernel<1024>: window move, 4-point-per-thread transform, bars and beat stage of two streams per CTA); tools/tick_bench.py times both forms"})
 
 # ---- c4: 16384-pt window, 512 bars, stereo (1 min), hop 512 and 4096
 pcm = torch.empty((2, 48000 * 60), dtype=torch.int16, device=dev)

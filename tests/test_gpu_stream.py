@@ -34,13 +34,20 @@ def move_array_exact(dest, fresh):
     return np.concatenate([dest[add:], fresh])
 
 
-@pytest.mark.parametrize("mode,n,tick", [("exact", 1024, "one_kernel"), ("exact", 2048, "one_kernel"), ("exact", 1024, "three_launches"),
-                                         ("exact", 4096, "three_launches"), ("reference", 1024, "three_launches")])
-def test_streaming_ticks_match_oracle(oracle, lib, mode, n, tick):
+@pytest.mark.parametrize("mode,n,tick,bars", [("exact", 1024, "one_kernel", 64), ("exact", 2048, "one_kernel", 64), ("exact", 1024, "three_launches", 64),
+                                              ("exact", 4096, "three_launches", 64), ("reference", 1024, "three_launches", 100),
+                                              ("exact", 1024, "one_kernel", 200),      # fewer lanes than 2 per bar: one lane per bar
+                                              ("exact_parity", 1024, "one_kernel", 400),  # more bars than threads, no window, no SG, bar i = bin i
+                                              ("exact_parity", 2048, "one_kernel", 100), ("exact_circle", 1024, "one_kernel", 32)])
+def test_streaming_ticks_match_oracle(oracle, lib, mode, n, tick, bars):
     """Every tick of every stream against the oracle, through both forms of a push: the one-kernel tick (stream_tick.cuh:
     n = 1024 / 2048 with the exact window move) and the three launches (window move, batched bars kernel, beat stage)."""
-    B, streams = 64, 7
-    cfg = lib.extended_config(n, 1024, B) if mode == "exact" else lib.reference_config(n, 1024, 100)
+    B, streams = bars, 7
+    cfg = lib.extended_config(n, 1024, B) if mode in ("exact", "exact_circle") else lib.reference_config(n, 1024, B)
+    if mode == "exact_circle":
+        cfg.circle = 1                                # heights + 10 (fft_lines.c:204-207)
+    if mode != "reference":
+        mode = "exact"
     B = cfg.bars
     oc = _ocfg(oracle, cfg)
     rng = np.random.default_rng(11)

@@ -1,5 +1,6 @@
 """Developer timing probe of the c3 streaming tick (1024 streams x 1024-pt): device time per tick by CUDA-graph replay."""
 import sys
+import time
 sys.path.insert(0, ".")
 import torch
 import fft_lines_b200 as F
@@ -28,12 +29,16 @@ for name, which in (("one kernel per tick", F.TICK_AUTO), ("three launches per t
                 for _ in range(50):
                     g.replay()
                 e0, e1 = torch.cuda.Event(enable_timing=True), torch.cuda.Event(enable_timing=True)
+                st.synchronize()
                 e0.record(st)
+                h0 = time.perf_counter()
                 for _ in range(1000 // TICKS):
                     g.replay()
+                h1 = time.perf_counter()   # the host's share: how fast it can submit replays at all
                 e1.record(st)
                 st.synchronize()
-                print("%s: %.2f us per tick (device, graph of %d tick(s) replayed back to back)" % (name, e0.elapsed_time(e1) * 1e3 / (1000 // TICKS * TICKS), TICKS))
+                print("%s: %.2f us per tick (device, graph of %d tick(s) replayed back to back; host submits one replay per %.2f us)"
+                      % (name, e0.elapsed_time(e1) * 1e3 / (1000 // TICKS * TICKS), TICKS, (h1 - h0) * 1e6 / (1000 // TICKS)))
 
 # the floor of this way of measuring: a graph of one (or eight) empty-ish kernel(s) replayed back to back
 one = torch.zeros(1, device=dev)

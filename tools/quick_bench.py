@@ -33,5 +33,6 @@ wall = (time.time() - t0) / K
 calls, tot, bk = sp.timing()
 # order-independent fingerprint of the outputs: A/B builds that claim bit-identical results must print the same one
 fp = int(out_bars.view(torch.int32).to(torch.int64).sum().item()) & 0xffffffffffff
+fp ^= (int(beat.to(torch.int64).sum().item()) & 0xffffffffffff) << 1   # the beat records too
 print("n=%d bars=%d mode=%s frames=%d  fp %012x  total %.3f ms  bars-kernel %.3f ms  wall %.3f ms  -> %.1f M frames/s (bars kernel %.1f M/s)"
       % (n, bars, mode, ch * nf, fp, tot / calls, bk / calls, wall * 1e3, ch * nf / (tot / calls) / 1e3, ch * nf / (bk / calls) / 1e3))

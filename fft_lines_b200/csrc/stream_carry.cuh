@@ -108,19 +108,28 @@ template <int LANES> __device__ __forceinline__ int stream_carry_peak(const int*
         }
         rank++;
     }
+    if constexpr (LANES == 32) {
+        // a whole warp per stream: three warp reductions instead of fifteen shuffles (largest value among the lanes that have
+        // a candidate -- a candidate's value is > 0 --, lowest index on a tie; the earliest peak of all as the fall-back)
+        const int m = __reduce_max_sync(mask, best_idx >= 0 ? best_val : 0);
+        const int idx = __reduce_min_sync(mask, (best_idx >= 0 && best_val == m) ? best_idx : (1 << 30));
+        first = __reduce_min_sync(mask, first);
+        return m > 0 ? idx : (first < (1 << 30) ? first : 0);
+    } else {
 #pragma unroll
-    for (int o = LANES / 2; o > 0; o >>= 1) {
-        int ov = __shfl_xor_sync(mask, best_val, o, LANES);
-        int oi = __shfl_xor_sync(mask, best_idx, o, LANES);
-        int of = __shfl_xor_sync(mask, first, o, LANES);
-        bool take = (oi >= 0) && (best_idx < 0 || ov > best_val || (ov == best_val && oi < best_idx));
-        if (take) {
-            best_val = ov;
-            best_idx = oi;
+        for (int o = LANES / 2; o > 0; o >>= 1) {
+            int ov = __shfl_xor_sync(mask, best_val, o, LANES);
+            int oi = __shfl_xor_sync(mask, best_idx, o, LANES);
+            int of = __shfl_xor_sync(mask, first, o, LANES);
+            bool take = (oi >= 0) && (best_idx < 0 || ov > best_val || (ov == best_val && oi < best_idx));
+            if (take) {
+                best_val = ov;
+                best_idx = oi;
+            }
+            first = of < first ? of : first;
         }
-        first = of < first ? of : first;
+        return best_idx >= 0 ? best_idx : (first < (1 << 30) ? first : 0);
     }
-    return best_idx >= 0 ? best_idx : (first < (1 << 30) ? first : 0);
 }
 
 // AddBeatSample (beatDetector.c:30-44) on stream ss's own ring and the tick's beat record: w / bass = this tick's band energy

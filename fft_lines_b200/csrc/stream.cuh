@@ -3,10 +3,12 @@
 // The reference keeps ONE sliding window of the last N samples per channel
 // (GetAudioBuffer + MoveArray, fft_lines/wasapi_audio.cpp:390-484) and runs one
 // WM_TIMER tick on it (fft_lines.c:186-236, :281).  Here `streams` such windows
-// and their beat state live on the device; one push = one tick for every stream:
+// and their beat state live on the device; one push = one tick for every stream.  For n = 1024 / 2048 with the exact
+// window move a push is ONE kernel laid out for latency (stream_tick.cuh); this file holds the three-launch form
+// every other case runs (and the one-kernel tick is tested against):
 //   stream_slide_kernel   MoveArray for all streams (exact, or with the reference's
 //                         off-by-one, wasapi_audio.cpp:394)
-//   stft_bars_kernel<N>   one frame per stream (kernels.cuh)
+//   bars kernel           one frame per stream (the fast path for n = 1024 ... 16384, else stft_bars_kernel<N>)
 //   stream_beat_carry_kernel  AddBeatSample + BassBeatDetector on per-stream rings
 // All three take their positions from a device-resident tick counter (advanced by the last CTA
 // of the push's last kernel), so the triple can be captured once in a CUDA graph and replayed every tick.

@@ -382,6 +382,29 @@ def latency_leg(F, dev):
             e1.record(st)
             st.synchronize()
             dev_us8 = e0.elapsed_time(e1) * 1e3 / 800
+        # the three-launch form of a push (window move, batched bars kernel, beat stage) timed the same way, for comparison
+        dev_us_three = None
+        try:
+            with F.StreamingSpectrum(cfg3, STREAMS, device=dev.index) as s3:
+                s3.set_tick_kernel(F.TICK_THREE_LAUNCHES)
+                with torch.cuda.stream(st):
+                    for _ in range(5):
+                        s3.push_device(fresh, bars, None, beat, stream=st)
+                    st.synchronize()
+                    g3 = torch.cuda.CUDAGraph()
+                    with torch.cuda.graph(g3, stream=st):
+                        s3.push_device(fresh, bars, None, beat, stream=st)
+                    for _ in range(50):
+                        g3.replay()
+                    e0.record(st)
+                    for _ in range(500):
+                        g3.replay()
+                    e1.record(st)
+                    st.synchronize()
+                    dev_us_three = e0.elapsed_time(e1) * 1e3 / 500
+                    del g3
+        except Exception as ex:  # a comparison figure only: never fails the bench
+            sys.stderr.write("latency: three-launch comparison skipped (%s)\n" % ex)
         h_fresh = F.PinnedArray((STREAMS, COUNT), np.int16)
         h_fresh.array[:] = fresh.cpu().numpy()
         hb, hbt = F.PinnedArray((STREAMS, B), np.float32), F.PinnedArray((STREAMS,), F.BEAT_DTYPE)
@@ -397,7 +420,7 @@ def latency_leg(F, dev):
         h_fresh.free(); hb.free(); hbt.free()
     return {"workload": "c3: 1024 concurrent mono streams, 1024-pt Hann, 64 log bars + SG + beat, one tick (512 new samples per stream) per batch",
             "frames_per_batch": STREAMS, "kernels_per_tick": int(per_tick),
-            "device_us_per_batch": dev_us, "device_us_per_batch_8_ticks_per_graph": dev_us8, "frames_per_s_device": STREAMS / dev_us * 1e6,
+            "device_us_per_batch": dev_us, "device_us_per_batch_8_ticks_per_graph": dev_us8, "device_us_per_batch_three_launches": dev_us_three, "frames_per_s_device": STREAMS / dev_us * 1e6,
             "tick_kernel": "stream_tick_kernel<1024> (one kernel per tick: csrc/stream_tick.cuh)" if per_tick == 1 else "window move + bars kernel + beat stage",
             "graph_replay_plus_sync": pct(lat_graph), "host_buffer_call": pct(lat_host),
             "note": "device = CUDA-graph replays back to back (events); graph_replay_plus_sync = one replay + stream sync seen "

@@ -13,8 +13,9 @@
 //     zoom, (int) heights, band energy and bass bin (fft_lines.c:195-208, :281; beatDetector.c:53);
 //   * AddBeatSample / BassBeatDetector on the streams' rings with the carried tempo transform (stream_carry.cuh): the ring
 //     state is fetched at the start of the kernel, the bins are updated between the untangling and the bars, the peak scan
-//     runs on the last warp beside the Savitzky-Golay step; the CTA that arrives last at the device-resident tick counter
-//     advances it (the arrival itself is made at the start, so its round trip is off the tail).
+//     runs on the last two warps (32 lanes per stream, warp reductions) beside the Savitzky-Golay step; the CTA that
+//     arrives last at the device-resident tick counter advances it (the arrival itself is made at the start, so its round
+//     trip is off the tail).
 // Used for N = 1024 and 2048 with the exact window move; every other case keeps the three launches.
 #pragma once
 #include "kernels.cuh"
@@ -136,7 +137,7 @@ __global__ void __launch_bounds__(N / 4, 4096 / N) stream_tick_kernel(const Stft
     const int w = p.sg_half, m = 2 * w + 1;
     if (w > 0)
         for (int i = g; i < m * m; i += G) cp_async4(t_sg + i, p.sg + i);
-    // ---- everything that depends on the tick, behind the loads that do not (the asm's memory clobber keeps them in front)
+    // ---- everything that depends on the tick, behind the loads that do not
     // The tick counter is read exactly once, through the L1 (one L2 request per SM instead of one per warp on one L2
     // line; the counter changes only once every CTA has its copy, and the next kernel starts with a clean L1).  The CTA
     // that arrives last at `done` advances it (stream_finish), and a CTA may arrive as soon as it has its copy: the
